@@ -1,0 +1,149 @@
+/*
+ * smirk_b200 — C ABI of the B200-native SMIRK hot path (encode -> FLAME -> render -> generator).
+ *
+ * The reference (georgeretsi/smirk) is pure Python and has no FFI of its own; its only native seams
+ * on this path are third-party: `timm.create_model` (src/smirk_encoder.py:7-12), ATen/cuDNN ops, and
+ * `pytorch3d.renderer.mesh.rasterize_meshes` (src/renderer/renderer.py:185-193).  Each entry point
+ * below replaces the body of one reference nn.Module.forward; the Python classes in smirk_b200/ keep
+ * the reference signatures and call these through ctypes (see INTEGRATION.md for the binding).
+ *
+ * Conventions
+ *   - return 0 = OK, <0 = argument/shape error, >0 = cudaError_t; message via smk_last_error()
+ *     (thread-local).  No exceptions, no exit().
+ *   - `*_create` take HOST pointers to fp32 / int32 constant arrays, fold/pack them and upload to the
+ *     CURRENT CUDA device; handles are immutable afterwards.  `*_forward` take DEVICE pointers
+ *     (contiguous, 16-byte aligned), never allocate, never synchronise, and enqueue all work on the
+ *     caller's stream (cudaStream_t passed as void*) — CUDA-graph capturable.
+ *   - the caller owns inputs, outputs and the workspace (size from `*_workspace_bytes`).
+ */
+#ifndef SMIRK_B200_H
+#define SMIRK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMK_VERSION 100
+
+int smk_version(void);
+const char* smk_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * FLAME  — replaces FLAME.forward (src/FLAME/FLAME.py:232-315) and lbs() (src/FLAME/lbs.py:140-227).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct SmkFlame SmkFlame;
+
+typedef struct {
+    int n_verts;            /* 5023 */
+    int n_faces;            /* 9976 */
+    int n_betas;            /* n_shape + n_exp = 350 */
+    int n_joints;           /* 5, kinematic parents fixed to [-1,0,1,1,1] (FLAME.py:76-77) */
+    const float* v_template;        /* [V,3]                FLAME.py:64 */
+    const float* shapedirs;         /* [V,3,n_betas]        FLAME.py:67-69 */
+    const float* posedirs;          /* [(J-1)*9, V*3]       FLAME.py:71-73 */
+    const float* J_regressor;       /* [J,V]                FLAME.py:75 */
+    const float* lbs_weights;       /* [V,J]                FLAME.py:78 */
+    const float* l_eyelid;          /* [V,3]                FLAME.py:81 */
+    const float* r_eyelid;          /* [V,3]                FLAME.py:82 */
+    const int32_t* faces;           /* [F,3]                FLAME.py:61 */
+    /* landmark embeddings (FLAME.py:94-113) */
+    int n_static;  const int32_t* static_faces;  const float* static_bary;     /* 51 */
+    int n_dyn_rows; int n_dyn; const int32_t* dyn_faces; const float* dyn_bary; /* 79 x 17 */
+    int n_full;    const int32_t* full_faces;    const float* full_bary;       /* 68 */
+    int n_mp;      const int32_t* mp_faces;      const float* mp_bary;         /* 105 */
+} SmkFlameDesc;
+
+int smk_flame_create(const SmkFlameDesc* desc, SmkFlame** out);
+void smk_flame_destroy(SmkFlame* h);
+size_t smk_flame_workspace_bytes(const SmkFlame* h, int B);
+/* betas [B,n_betas] = cat(shape, expression); full_pose [B,15] = cat(global, neck, jaw, eyes(6));
+ * eyelid [B,2] or NULL.  Outputs: verts [B,V,3]; lmk_fan [B,68,3] (17 dynamic-contour + 51 static);
+ * lmk_fan3d [B,68,3]; lmk_mp [B,105,3]; joints [B,J,3] (posed joints, may be NULL);
+ * dyn_idx int32 [B] (selected contour LUT row, may be NULL).                                     */
+int smk_flame_forward(const SmkFlame* h, const float* betas, const float* full_pose, const float* eyelid,
+                      int B, float* verts, float* lmk_fan, float* lmk_fan3d, float* lmk_mp,
+                      float* joints, int32_t* dyn_idx, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Renderer — replaces Renderer.forward/render/rasterize (src/renderer/renderer.py:100-207,239-250),
+ * util.vertex_normals/face_vertices/batch_orth_proj (src/renderer/util.py) and the third-party
+ * pytorch3d rasterize_meshes call (renderer.py:185-193; blur 0, K=1, no perspective correction).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct SmkRenderer SmkRenderer;
+
+typedef struct {
+    int n_verts;               /* vertices of the incoming mesh (5023) */
+    int n_mask;                /* rendered subset (1787 for the FLAME `face` mask; = n_verts for full head) */
+    const int32_t* mask_ids;   /* [n_mask] vertex ids, order defines the sub-mesh numbering (renderer.py:71) */
+    int n_faces;               /* 3408 */
+    const int32_t* faces;      /* [n_faces,3] indices into the sub-mesh (renderer.py:74) */
+    int image_size;            /* 224 */
+} SmkRendererDesc;
+
+int smk_renderer_create(const SmkRendererDesc* desc, SmkRenderer** out);
+void smk_renderer_destroy(SmkRenderer* h);
+size_t smk_renderer_workspace_bytes(const SmkRenderer* h, int B);
+/* verts [B,n_verts,3], cam [B,3] = (scale, tx, ty).  Outputs: rendered [B,3,S,S]; tverts [B,n_verts,3];
+ * optional (NULL to skip): pix_to_face int64 [B,S,S] (packed b*n_faces+f, -1 = background),
+ * bary [B,S,S,3], zbuf [B,S,S] (both -1 on background), normals [B,n_mask,3].                       */
+int smk_renderer_forward(const SmkRenderer* h, const float* verts, const float* cam, int B,
+                         float* rendered, float* tverts, int64_t* pix_to_face, float* bary, float* zbuf,
+                         float* normals, void* ws, size_t ws_bytes, void* stream);
+/* Orthographic projection of landmark sets (renderer.py:104-108): pts [B,L,3] -> out [B,L,2]. */
+int smk_project_points(const float* pts, const float* cam, int B, int L, float* out_xy, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SmirkEncoder — replaces SmirkEncoder.forward (src/smirk_encoder.py:123-133): three timm
+ * tf_mobilenetv3_{small,large,large}_minimal_100 backbones (features_only, last feature) -> global
+ * average pool -> Linear heads -> split/clamps (:34-45,66-73,95-110).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct SmkEncoder SmkEncoder;
+
+typedef struct {
+    /* Per backbone (0 = pose/small, 1 = shape/large, 2 = expression/large): the fp32 tensors of its
+     * `encoder.*` state_dict in state_dict order with `num_batches_tracked` entries removed, i.e.
+     * conv weight [Cout,Cin/groups,k,k] followed by BN weight, bias, running_mean, running_var.       */
+    const float* const* tensors[3];
+    int n_tensors[3];
+    const float* head_w[3];    /* [6,576], [n_shape,960], [n_exp+5,960] */
+    const float* head_b[3];
+    int n_shape;               /* 300 */
+    int n_exp;                 /* 50 */
+    int precision;             /* 0 = fp32 CUDA-core GEMMs, 1 = TF32 tcgen05 GEMMs for the 1x1 convs */
+} SmkEncoderDesc;
+
+int smk_encoder_create(const SmkEncoderDesc* desc, SmkEncoder** out);
+void smk_encoder_destroy(SmkEncoder* h);
+size_t smk_encoder_workspace_bytes(const SmkEncoder* h, int B);
+/* img [B,3,224,224] NCHW in [0,1].  Outputs: pose_cam [B,6], shape [B,n_shape], expr [B,n_exp+5]
+ * with the clamps of smirk_encoder.py:105-108 already applied to columns n_exp..n_exp+4.           */
+int smk_encoder_forward(const SmkEncoder* h, const float* img, int B, float* pose_cam, float* shape,
+                        float* expr, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SmirkGenerator — replaces SmirkGenerator.forward (src/smirk_generator.py:51-86), eval-mode BN.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct SmkGenerator SmkGenerator;
+
+typedef struct {
+    int in_channels, out_channels, init_features, res_blocks;    /* 6, 3, 32, 5 (demo.py:63) */
+    /* fp32 tensors of the module's state_dict in state_dict order, `num_batches_tracked` removed.    */
+    const float* const* tensors;
+    int n_tensors;
+    int precision;             /* 0 = fp32 CUDA-core implicit GEMM, 1 = TF32 tcgen05 implicit GEMM */
+} SmkGeneratorDesc;
+
+int smk_generator_create(const SmkGeneratorDesc* desc, SmkGenerator** out);
+void smk_generator_destroy(SmkGenerator* h);
+size_t smk_generator_workspace_bytes(const SmkGenerator* h, int B);
+/* x [B,in_channels,224,224] NCHW -> y [B,out_channels,224,224] NCHW in (0,1). */
+int smk_generator_forward(const SmkGenerator* h, const float* x, int B, float* y,
+                          void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMIRK_B200_H */

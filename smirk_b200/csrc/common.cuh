@@ -1,0 +1,62 @@
+// Shared helpers for the smirk_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include "../../include/smirk_b200.h"
+
+namespace smk {
+
+void set_error(const char* fmt, ...);
+
+#define SMK_CHECK_CUDA(expr)                                                            \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            smk::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return (int)_e;                                                             \
+        }                                                                               \
+    } while (0)
+
+#define SMK_REQUIRE(cond, ...)                                                          \
+    do {                                                                                \
+        if (!(cond)) { smk::set_error(__VA_ARGS__); return -1; }                        \
+    } while (0)
+
+#define SMK_CHECK_LAUNCH() SMK_CHECK_CUDA(cudaGetLastError())
+
+// Device buffers owned by a handle (constants only; forwards never allocate).
+struct DeviceArena {
+    std::vector<void*> ptrs;
+    ~DeviceArena() { for (void* p : ptrs) cudaFree(p); }
+    template <typename T>
+    cudaError_t upload(const T* host, size_t n, T** out) {
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, n * sizeof(T) + 16);
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(d);
+        e = cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice);
+        *out = (T*)d;
+        return e;
+    }
+    template <typename T>
+    cudaError_t upload(const std::vector<T>& v, T** out) { return upload(v.data(), v.size(), out); }
+};
+
+// Bump allocator over the caller-provided workspace (256-byte aligned slices).
+struct Workspace {
+    char* base; size_t size; size_t off = 0;
+    Workspace(void* p, size_t n) : base((char*)p), size(n) {}
+    template <typename T> T* take(size_t n) {
+        size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+        if (off + bytes > size) return nullptr;
+        T* r = (T*)(base + off); off += bytes; return r;
+    }
+};
+static inline size_t ws_round(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace smk

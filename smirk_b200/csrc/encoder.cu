@@ -1,0 +1,205 @@
+// SmirkEncoder forward: three MobileNetV3-"minimal" backbones + pooled linear heads.
+//
+// Replaces SmirkEncoder.forward (reference src/smirk_encoder.py:123-133) including the timm backbones
+// built at :7-12 (tf_mobilenetv3_small_minimal_100 for pose, ..._large_minimal_100 for shape and
+// expression; ReLU only, no squeeze-excite, 3x3 depthwise, BN eps 1e-3, TF-SAME padding) and the
+// heads/clamps at :34-45, :66-73, :95-110.  BatchNorm (eval mode) is folded into a per-channel
+// scale/bias applied in each convolution's epilogue; activations live in NHWC fp32.
+#include "nn_kernels.cuh"
+#include <math.h>
+
+namespace {
+
+using smk::ConvProblem;
+
+constexpr float kBnEps = 1e-3f;
+
+struct ConvW { float* w = nullptr; float* scale = nullptr; float* bias = nullptr; int cin = 0, cout = 0; };
+enum Kind { DS = 0, IR = 1, CN = 2 };
+struct BlockDef { Kind kind; int stride; float exp; int cout; };
+struct Block { Kind kind; int stride, cin, mid, cout; bool skip; ConvW pw, dw, pwl; };
+
+struct Backbone {
+    ConvW stem;
+    std::vector<Block> blocks;
+    int feat = 0;
+    float *head_w = nullptr, *head_b = nullptr;
+    int n_out = 0;
+    uint8_t* codes = nullptr;
+};
+
+const BlockDef kLarge[] = {
+    {DS, 1, 1.f, 16},
+    {IR, 2, 4.f, 24}, {IR, 1, 3.f, 24},
+    {IR, 2, 3.f, 40}, {IR, 1, 3.f, 40}, {IR, 1, 3.f, 40},
+    {IR, 2, 6.f, 80}, {IR, 1, 2.5f, 80}, {IR, 1, 2.3f, 80}, {IR, 1, 2.3f, 80},
+    {IR, 1, 6.f, 112}, {IR, 1, 6.f, 112},
+    {IR, 2, 6.f, 160}, {IR, 1, 6.f, 160}, {IR, 1, 6.f, 160},
+    {CN, 1, 1.f, 960}};
+const BlockDef kSmall[] = {
+    {DS, 2, 1.f, 16},
+    {IR, 2, 4.5f, 24}, {IR, 1, 3.67f, 24},
+    {IR, 2, 4.f, 40}, {IR, 1, 6.f, 40}, {IR, 1, 6.f, 40},
+    {IR, 1, 3.f, 48}, {IR, 1, 3.f, 48},
+    {IR, 2, 6.f, 96}, {IR, 1, 6.f, 96}, {IR, 1, 6.f, 96},
+    {CN, 1, 1.f, 576}};
+
+int make_divisible(double v, int divisor = 8) {
+    int nv = std::max(divisor, (int)(v + divisor / 2.0) / divisor * divisor);
+    if (nv < 0.9 * v) nv += divisor;
+    return nv;
+}
+
+// Consumes (conv weight, bn gamma, beta, mean, var) from the tensor list.
+struct TensorCursor {
+    const float* const* t; int n; int i = 0;
+    const float* next() { return i < n ? t[i++] : nullptr; }
+};
+
+// kind: 0 = 1x1 [Cout,Cin,1,1] -> W[Cin][Cout]; 1 = depthwise [C,1,3,3] -> W[9][C]; 2 = stem [16,3,3,3] -> W[27][16]
+bool fold_conv(TensorCursor& cur, int kind, int cin, int cout, smk::DeviceArena& arena, ConvW* out, cudaError_t* err) {
+    const float* w = cur.next(); const float* g = cur.next(); const float* b = cur.next();
+    const float* mu = cur.next(); const float* var = cur.next();
+    if (!w || !g || !b || !mu || !var) return false;
+    std::vector<float> W, S(cout), Bi(cout);
+    if (kind == 0) {
+        W.resize((size_t)cin * cout);
+        for (int o = 0; o < cout; ++o) for (int c = 0; c < cin; ++c) W[(size_t)c * cout + o] = w[(size_t)o * cin + c];
+    } else if (kind == 1) {
+        W.resize((size_t)9 * cout);
+        for (int c = 0; c < cout; ++c) for (int k = 0; k < 9; ++k) W[(size_t)k * cout + c] = w[(size_t)c * 9 + k];
+    } else {
+        W.resize((size_t)27 * cout);
+        for (int o = 0; o < cout; ++o) for (int k = 0; k < 27; ++k) W[(size_t)k * cout + o] = w[(size_t)o * 27 + k];
+    }
+    for (int o = 0; o < cout; ++o) {
+        float s = g[o] / sqrtf(var[o] + kBnEps);
+        S[o] = s; Bi[o] = b[o] - mu[o] * s;
+    }
+    out->cin = cin; out->cout = cout;
+    cudaError_t e = arena.upload(W, &out->w);
+    if (e == cudaSuccess) e = arena.upload(S, &out->scale);
+    if (e == cudaSuccess) e = arena.upload(Bi, &out->bias);
+    *err = e;
+    return e == cudaSuccess;
+}
+
+}  // namespace
+
+struct SmkEncoder {
+    Backbone bb[3];
+    int n_shape = 300, n_exp = 50, precision = 0;
+    size_t max_act = 0;          // floats per image of the largest activation
+    smk::DeviceArena arena;
+};
+
+extern "C" int smk_encoder_create(const SmkEncoderDesc* desc, SmkEncoder** out) {
+    SMK_REQUIRE(desc && out, "smk_encoder_create: null argument");
+    SMK_REQUIRE(desc->precision == 0, "smk_encoder_create: precision %d not available for the encoder yet", desc->precision);
+    SmkEncoder* h = new SmkEncoder();
+    h->n_shape = desc->n_shape; h->n_exp = desc->n_exp; h->precision = desc->precision;
+    const int n_outs[3] = {6, desc->n_shape, desc->n_exp + 5};
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 3; ++i) {
+        const BlockDef* defs = i == 0 ? kSmall : kLarge;
+        const int nb = i == 0 ? (int)(sizeof(kSmall) / sizeof(BlockDef)) : (int)(sizeof(kLarge) / sizeof(BlockDef));
+        Backbone& bb = h->bb[i];
+        TensorCursor cur{desc->tensors[i], desc->n_tensors[i]};
+        bool ok = fold_conv(cur, 2, 3, 16, h->arena, &bb.stem, &e);
+        int cin = 16, res = 112;
+        size_t max_act = (size_t)112 * 112 * 16;
+        for (int k = 0; ok && k < nb; ++k) {
+            Block b{};
+            b.kind = defs[k].kind; b.stride = defs[k].stride; b.cin = cin; b.cout = defs[k].cout;
+            b.skip = b.kind != CN && b.stride == 1 && b.cin == b.cout;
+            if (b.kind == DS) {
+                b.mid = cin;
+                ok = fold_conv(cur, 1, cin, cin, h->arena, &b.dw, &e) && fold_conv(cur, 0, cin, b.cout, h->arena, &b.pw, &e);
+            } else if (b.kind == IR) {
+                b.mid = make_divisible((double)cin * defs[k].exp);
+                ok = fold_conv(cur, 0, cin, b.mid, h->arena, &b.pw, &e) && fold_conv(cur, 1, b.mid, b.mid, h->arena, &b.dw, &e) &&
+                     fold_conv(cur, 0, b.mid, b.cout, h->arena, &b.pwl, &e);
+            } else {
+                b.mid = cin;
+                ok = fold_conv(cur, 0, cin, b.cout, h->arena, &b.pw, &e);
+            }
+            max_act = std::max(max_act, (size_t)res * res * b.mid);           // expanded tensor at input resolution
+            res = (res + b.stride - 1) / b.stride;
+            max_act = std::max(max_act, (size_t)res * res * std::max(b.mid, b.cout));
+            cin = b.cout;
+            bb.blocks.push_back(b);
+        }
+        if (!ok || cur.i != cur.n) {
+            if (e != cudaSuccess) smk::set_error("smk_encoder_create: upload failed: %s", cudaGetErrorString(e));
+            else smk::set_error("smk_encoder_create: backbone %d expects %d tensors (conv weight + 4 BN tensors per conv), got %d",
+                                i, cur.i, cur.n);
+            delete h; return e != cudaSuccess ? (int)e : -1;
+        }
+        bb.feat = cin; bb.n_out = n_outs[i];
+        h->max_act = std::max(h->max_act, max_act);
+        e = h->arena.upload(desc->head_w[i], (size_t)bb.n_out * bb.feat, &bb.head_w);
+        if (e == cudaSuccess) e = h->arena.upload(desc->head_b[i], (size_t)bb.n_out, &bb.head_b);
+        if (i == 2 && e == cudaSuccess) {                  // smirk_encoder.py:105-108
+            std::vector<uint8_t> codes(bb.n_out, 0);
+            int ne = desc->n_exp;
+            codes[ne] = codes[ne + 1] = 1; codes[ne + 2] = 2; codes[ne + 3] = codes[ne + 4] = 3;
+            e = h->arena.upload(codes, &bb.codes);
+        }
+        if (e != cudaSuccess) { smk::set_error("smk_encoder_create: upload failed: %s", cudaGetErrorString(e)); delete h; return (int)e; }
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" void smk_encoder_destroy(SmkEncoder* h) { delete h; }
+
+extern "C" size_t smk_encoder_workspace_bytes(const SmkEncoder* h, int B) {
+    return 4 * smk::ws_round((size_t)B * h->max_act * sizeof(float));
+}
+
+static int pointwise(const ConvW& c, const float* in, int B, int H, int W, bool relu, const float* res, float* out, cudaStream_t st) {
+    ConvProblem p{};
+    p.in = in; p.ld_in = c.cin; p.B = B; p.H = H; p.W = W; p.Cin = c.cin;
+    p.w = c.w; p.scale = c.scale; p.bias = c.bias; p.N = c.cout; p.K = c.cin; p.mode = 0; p.relu = relu ? 1 : 0;
+    p.res = res; p.ld_res = c.cout; p.out = out; p.ld_out = c.cout; p.shuffle = 0;
+    return smk::conv_gemm(p, st);
+}
+
+extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B, float* pose_cam, float* shape,
+                                   float* expr, void* ws, size_t ws_bytes, void* stream) {
+    SMK_REQUIRE(h && img && pose_cam && shape && expr, "smk_encoder_forward: null argument");
+    if (B == 0) return 0;
+    SMK_REQUIRE(B > 0, "smk_encoder_forward: negative batch");
+    SMK_REQUIRE(ws && ws_bytes >= smk_encoder_workspace_bytes(h, B), "smk_encoder_forward: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    smk::Workspace w(ws, ws_bytes);
+    float* buf[4];
+    for (int i = 0; i < 4; ++i) buf[i] = w.take<float>((size_t)B * h->max_act);
+    float* outs[3] = {pose_cam, shape, expr};
+    for (int i = 0; i < 3; ++i) {
+        const Backbone& bb = h->bb[i];
+        float *x = buf[0], *y = buf[1], *e = buf[2], *d = buf[3];
+        int rc = smk::stem_conv(img, B, 224, 224, bb.stem.w, bb.stem.scale, bb.stem.bias, x, st);
+        if (rc) return rc;
+        int res = 112;
+        for (const Block& b : bb.blocks) {
+            int ro = (res + b.stride - 1) / b.stride;
+            if (b.kind == DS) {
+                rc = smk::dwconv3x3(x, B, res, res, b.cin, b.stride, b.dw.w, b.dw.scale, b.dw.bias, d, st);
+                if (!rc) rc = pointwise(b.pw, d, B, ro, ro, false, b.skip ? x : nullptr, y, st);
+            } else if (b.kind == IR) {
+                rc = pointwise(b.pw, x, B, res, res, true, nullptr, e, st);
+                if (!rc) rc = smk::dwconv3x3(e, B, res, res, b.mid, b.stride, b.dw.w, b.dw.scale, b.dw.bias, d, st);
+                if (!rc) rc = pointwise(b.pwl, d, B, ro, ro, false, b.skip ? x : nullptr, y, st);
+            } else {
+                rc = pointwise(b.pw, x, B, res, res, true, nullptr, y, st);
+            }
+            if (rc) return rc;
+            std::swap(x, y);
+            res = ro;
+        }
+        rc = smk::gap_linear(x, B, res * res, bb.feat, bb.head_w, bb.head_b, bb.n_out, bb.codes, outs[i], st);
+        if (rc) return rc;
+    }
+    return 0;
+}

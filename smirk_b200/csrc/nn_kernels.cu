@@ -1,0 +1,368 @@
+// fp32 CUDA-core kernels for the encoder / generator (see nn_kernels.cuh).
+#include "nn_kernels.cuh"
+
+namespace smk {
+namespace {
+
+constexpr int BK = 16;
+constexpr int NT = 256;
+
+// ---------------------------------------------------------------------------------------------------
+// Implicit-GEMM convolution, BMxBN tile, BK = 16, 256 threads as a 16x16 grid of (BM/16)x(BN/16)
+// register tiles; global->register prefetch of the next k-slab overlaps the FMAs of the current one.
+template <int BM, int BN>
+__global__ void __launch_bounds__(NT)
+conv_gemm_kernel(ConvProblem p, int M) {
+    constexpr int TM = BM / 16, TN = BN / 16;
+    constexpr int A_LD = BM + 4, B_LD = BN + 4;
+    constexpr int A_PER = BM / 64;                 // float4 loads of A per thread per slab (BM*BK/4/NT)
+    constexpr int B_PER = (BN * BK / 4 + NT - 1) / NT;
+    __shared__ __align__(16) float As[BK][A_LD];
+    __shared__ __align__(16) float Bs[BK][B_LD];
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int HW = p.H * p.W;
+
+    // per-thread A rows: r = tid/4 + 64*j, k-quad kq = tid%4
+    const int kq = tid & 3;
+    int a_b[A_PER], a_h[A_PER], a_w[A_PER];
+    bool a_ok[A_PER];
+#pragma unroll
+    for (int j = 0; j < A_PER; ++j) {
+        int m = m0 + (tid >> 2) + 64 * j;
+        a_ok[j] = m < M;
+        int mm = a_ok[j] ? m : 0;
+        a_b[j] = mm / HW; int r = mm - a_b[j] * HW; a_h[j] = r / p.W; a_w[j] = r - a_h[j] * p.W;
+    }
+    float4 a_reg[A_PER], b_reg[B_PER];
+
+    auto load_slab = [&](int k0) {
+        const int k = k0 + kq * 4;
+#pragma unroll
+        for (int j = 0; j < A_PER; ++j) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a_ok[j] && k < p.K) {
+                if (p.mode == 0) {
+                    v = *reinterpret_cast<const float4*>(p.in + ((size_t)(a_b[j] * HW + a_h[j] * p.W + a_w[j])) * p.ld_in + k);
+                } else {
+                    int tap = k / p.Cin, c = k - tap * p.Cin;
+                    int ky = tap / 3, kx = tap - ky * 3;
+                    int hh = a_h[j] + ky - 1, ww = a_w[j] + kx - 1;
+                    bool inside = hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;
+                    if (p.mode == 2) {                                  // ReflectionPad2d(1)
+                        hh = hh < 0 ? 1 : (hh >= p.H ? p.H - 2 : hh);
+                        ww = ww < 0 ? 1 : (ww >= p.W ? p.W - 2 : ww);
+                        inside = true;
+                    }
+                    if (inside)
+                        v = *reinterpret_cast<const float4*>(p.in + ((size_t)(a_b[j] * p.H + hh) * p.W + ww) * p.ld_in + c);
+                }
+            }
+            a_reg[j] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < B_PER; ++j) {
+            int idx = tid + j * NT;                     // float4 index within the BK x BN slab
+            int kk = idx / (BN / 4), nq = idx - kk * (BN / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kk < BK && k0 + kk < p.K && n0 + nq * 4 < p.N)
+                v = *reinterpret_cast<const float4*>(p.w + (size_t)(k0 + kk) * p.N + n0 + nq * 4);
+            b_reg[j] = v;
+        }
+    };
+    auto store_slab = [&]() {
+#pragma unroll
+        for (int j = 0; j < A_PER; ++j) {
+            int r = (tid >> 2) + 64 * j;
+            As[kq * 4 + 0][r] = a_reg[j].x; As[kq * 4 + 1][r] = a_reg[j].y;
+            As[kq * 4 + 2][r] = a_reg[j].z; As[kq * 4 + 3][r] = a_reg[j].w;
+        }
+#pragma unroll
+        for (int j = 0; j < B_PER; ++j) {
+            int idx = tid + j * NT;
+            int kk = idx / (BN / 4), nq = idx - kk * (BN / 4);
+            if (kk < BK) *reinterpret_cast<float4*>(&Bs[kk][nq * 4]) = b_reg[j];
+        }
+    };
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    load_slab(0);
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
+        __syncthreads();
+        store_slab();
+        __syncthreads();
+        if (k0 + BK < p.K) load_slab(k0 + BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+    }
+    // epilogue
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        int m = m0 + ty * TM + i;
+        if (m >= M) continue;
+        size_t opix = m;
+        int nbase = n0 + tx * TN;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            int n = nbase + j;
+            if (n >= p.N) continue;
+            float v = fmaf(acc[i][j], p.scale[n], p.bias[n]);
+            if (p.res) v += p.res[(size_t)m * p.ld_res + n];
+            if (p.relu) v = fmaxf(v, 0.f);
+            if (p.shuffle) {
+                int cout = p.N >> 2, q = n / cout, co = n - q * cout;
+                int b = m / HW, r = m - b * HW, h = r / p.W, w = r - h * p.W;
+                size_t dp = ((size_t)b * (2 * p.H) + 2 * h + (q >> 1)) * (2 * p.W) + 2 * w + (q & 1);
+                p.out[dp * p.ld_out + co] = v;
+            } else {
+                p.out[opix * p.ld_out + n] = v;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dwconv3x3_kernel(const float* __restrict__ in, int B, int H, int W, int C, int stride, int pad, int Ho, int Wo,
+                 const float* __restrict__ w9c, const float* __restrict__ scale, const float* __restrict__ bias,
+                 float* __restrict__ out) {
+    const int C4 = C >> 2;
+    const long total = (long)B * Ho * Wo * C4;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int c4 = (int)(i % C4); long pix = i / C4;
+        int ow = (int)(pix % Wo); long t = pix / Wo; int oh = (int)(t % Ho); int b = (int)(t / Ho);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            int ih = oh * stride + ky - pad;
+            if (ih < 0 || ih >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                int iw = ow * stride + kx - pad;
+                if (iw < 0 || iw >= W) continue;
+                float4 x = *reinterpret_cast<const float4*>(in + (((size_t)b * H + ih) * W + iw) * C + c4 * 4);
+                float4 k = *reinterpret_cast<const float4*>(w9c + (size_t)(ky * 3 + kx) * C + c4 * 4);
+                acc.x = fmaf(x.x, k.x, acc.x); acc.y = fmaf(x.y, k.y, acc.y);
+                acc.z = fmaf(x.z, k.z, acc.z); acc.w = fmaf(x.w, k.w, acc.w);
+            }
+        }
+        float4 s = *reinterpret_cast<const float4*>(scale + c4 * 4), bb = *reinterpret_cast<const float4*>(bias + c4 * 4);
+        float4 o;
+        o.x = fmaxf(fmaf(acc.x, s.x, bb.x), 0.f); o.y = fmaxf(fmaf(acc.y, s.y, bb.y), 0.f);
+        o.z = fmaxf(fmaf(acc.z, s.z, bb.z), 0.f); o.w = fmaxf(fmaf(acc.w, s.w, bb.w), 0.f);
+        *reinterpret_cast<float4*>(out + (size_t)pix * C + c4 * 4) = o;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+stem_conv_kernel(const float* __restrict__ img, int B, int H, int W, int Ho, int Wo, int pad,
+                 const float* __restrict__ w /*[27][16]*/, const float* __restrict__ scale,
+                 const float* __restrict__ bias, float* __restrict__ out) {
+    __shared__ float sw[27 * 16];
+    __shared__ float ss[16], sb[16];
+    for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) sw[i] = w[i];
+    if (threadIdx.x < 16) { ss[threadIdx.x] = scale[threadIdx.x]; sb[threadIdx.x] = bias[threadIdx.x]; }
+    __syncthreads();
+    long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (long)B * Ho * Wo) return;
+    int ow = (int)(pix % Wo); long t = pix / Wo; int oh = (int)(t % Ho); int b = (int)(t / Ho);
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            int ih = oh * 2 + ky - pad;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                int iw = ow * 2 + kx - pad;
+                float x = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? img[(((size_t)b * 3 + c) * H + ih) * W + iw] : 0.f;
+                const float* wk = sw + ((c * 3 + ky) * 3 + kx) * 16;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] = fmaf(x, wk[i], acc[i]);
+            }
+        }
+    float4* o = reinterpret_cast<float4*>(out + (size_t)pix * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float4 v;
+        v.x = fmaxf(fmaf(acc[q * 4 + 0], ss[q * 4 + 0], sb[q * 4 + 0]), 0.f);
+        v.y = fmaxf(fmaf(acc[q * 4 + 1], ss[q * 4 + 1], sb[q * 4 + 1]), 0.f);
+        v.z = fmaxf(fmaf(acc[q * 4 + 2], ss[q * 4 + 2], sb[q * 4 + 2]), 0.f);
+        v.w = fmaxf(fmaf(acc[q * 4 + 3], ss[q * 4 + 3], sb[q * 4 + 3]), 0.f);
+        o[q] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+maxpool2x2_kernel(const float* __restrict__ in, int ld_in, int B, int H, int W, int C, float* __restrict__ out) {
+    const int Ho = H >> 1, Wo = W >> 1, C4 = C >> 2;
+    const long total = (long)B * Ho * Wo * C4;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int c4 = (int)(i % C4); long pix = i / C4;
+        int ow = (int)(pix % Wo); long t = pix / Wo; int oh = (int)(t % Ho); int b = (int)(t / Ho);
+        const float* p00 = in + (((size_t)b * H + 2 * oh) * W + 2 * ow) * ld_in + c4 * 4;
+        float4 a = *reinterpret_cast<const float4*>(p00), bq = *reinterpret_cast<const float4*>(p00 + ld_in);
+        float4 c = *reinterpret_cast<const float4*>(p00 + (size_t)W * ld_in), d = *reinterpret_cast<const float4*>(p00 + (size_t)W * ld_in + ld_in);
+        float4 o;
+        o.x = fmaxf(fmaxf(a.x, bq.x), fmaxf(c.x, d.x)); o.y = fmaxf(fmaxf(a.y, bq.y), fmaxf(c.y, d.y));
+        o.z = fmaxf(fmaxf(a.z, bq.z), fmaxf(c.z, d.z)); o.w = fmaxf(fmaxf(a.w, bq.w), fmaxf(c.w, d.w));
+        *reinterpret_cast<float4*>(out + (size_t)pix * C + c4 * 4) = o;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_pad_kernel(const float* __restrict__ in, int B, int C, int HW, int Cp, float* __restrict__ out) {
+    long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (long)B * HW) return;
+    int b = (int)(pix / HW); int r = (int)(pix - (long)b * HW);
+    for (int c = 0; c < Cp; ++c)
+        out[(size_t)pix * Cp + c] = c < C ? in[((size_t)b * C + c) * HW + r] : 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+conv1x1_sigmoid_kernel(const float* __restrict__ in, int B, int HW, int Cin, const float* __restrict__ w,
+                       const float* __restrict__ bias, int Cout, float* __restrict__ out) {
+    extern __shared__ float sw[];                 // [Cin][Cout] + [Cout]
+    for (int i = threadIdx.x; i < Cin * Cout; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[Cin * Cout + i] = bias[i];
+    __syncthreads();
+    long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (long)B * HW) return;
+    int b = (int)(pix / HW); int r = (int)(pix - (long)b * HW);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4* x4 = reinterpret_cast<const float4*>(in + (size_t)pix * Cin);
+    for (int c4 = 0; c4 < Cin / 4; ++c4) {
+        float4 x = x4[c4];
+        float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            for (int co = 0; co < Cout; ++co) acc[co] = fmaf(xs[q], sw[(c4 * 4 + q) * Cout + co], acc[co]);
+    }
+    for (int co = 0; co < Cout; ++co) {
+        float v = acc[co] + sw[Cin * Cout + co];
+        out[((size_t)b * Cout + co) * HW + r] = 1.f / (1.f + expf(-v));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gap_linear_kernel(const float* __restrict__ feat, int HW, int C, const float* __restrict__ w, const float* __restrict__ bias,
+                  int n_out, const uint8_t* __restrict__ codes, float* __restrict__ out) {
+    extern __shared__ float pooled[];             // [C]
+    const int b = blockIdx.x;
+    const float* f = feat + (size_t)b * HW * C;
+    const float inv = 1.f / (float)HW;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int p = 0; p < HW; ++p) s += f[(size_t)p * C + c];
+        pooled[c] = s * inv;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int o = warp; o < n_out; o += nw) {
+        const float* wr = w + (size_t)o * C;
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32) acc = fmaf(pooled[c], wr[c], acc);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+        if (lane == 0) {
+            float v = acc + bias[o];
+            int code = codes ? codes[o] : 0;
+            if (code == 1) v = fminf(fmaxf(v, 0.f), 1.f);
+            else if (code == 2) v = fmaxf(v, 0.f);
+            else if (code == 3) v = fminf(fmaxf(v, -0.2f), 0.2f);
+            out[(size_t)b * n_out + o] = v;
+        }
+    }
+}
+
+}  // namespace
+
+int conv_gemm(const ConvProblem& p, cudaStream_t st) {
+    const int M = p.B * p.H * p.W;
+    SMK_REQUIRE(p.K % 4 == 0 && p.N % 4 == 0 && p.ld_in % 4 == 0, "conv_gemm: K, N, ld_in must be multiples of 4");
+    SMK_REQUIRE(p.mode == 0 || p.Cin % 4 == 0, "conv_gemm: Cin must be a multiple of 4");
+    if (p.N <= 32) {
+        dim3 grid(cdiv(M, 128), cdiv(p.N, 32));
+        conv_gemm_kernel<128, 32><<<grid, NT, 0, st>>>(p, M);
+    } else {
+        dim3 grid(cdiv(M, 64), cdiv(p.N, 64));
+        conv_gemm_kernel<64, 64><<<grid, NT, 0, st>>>(p, M);
+    }
+    SMK_CHECK_LAUNCH();
+    return 0;
+}
+
+static inline int same_pad_begin(int H, int stride) {
+    int out = (H + stride - 1) / stride;
+    int total = (out - 1) * stride + 3 - H;
+    if (total < 0) total = 0;
+    return total / 2;
+}
+
+int dwconv3x3(const float* in, int B, int H, int W, int C, int stride, const float* w9c, const float* scale,
+              const float* bias, float* out, cudaStream_t st) {
+    SMK_REQUIRE(C % 4 == 0, "dwconv3x3: C must be a multiple of 4");
+    int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+    long total = (long)B * Ho * Wo * (C / 4);
+    int blocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
+    dwconv3x3_kernel<<<blocks, 256, 0, st>>>(in, B, H, W, C, stride, same_pad_begin(H, stride), Ho, Wo, w9c, scale, bias, out);
+    SMK_CHECK_LAUNCH();
+    return 0;
+}
+
+int stem_conv(const float* img, int B, int H, int W, const float* w, const float* scale, const float* bias, float* out,
+              cudaStream_t st) {
+    int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    stem_conv_kernel<<<cdiv((long)B * Ho * Wo, 128), 128, 0, st>>>(img, B, H, W, Ho, Wo, same_pad_begin(H, 2), w, scale, bias, out);
+    SMK_CHECK_LAUNCH();
+    return 0;
+}
+
+int maxpool2x2(const float* in, int ld_in, int B, int H, int W, int C, float* out, cudaStream_t st) {
+    long total = (long)B * (H / 2) * (W / 2) * (C / 4);
+    int blocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
+    maxpool2x2_kernel<<<blocks, 256, 0, st>>>(in, ld_in, B, H, W, C, out);
+    SMK_CHECK_LAUNCH();
+    return 0;
+}
+
+int nchw_to_nhwc_pad(const float* in, int B, int C, int H, int W, int Cp, float* out, cudaStream_t st) {
+    nchw_to_nhwc_pad_kernel<<<cdiv((long)B * H * W, 256), 256, 0, st>>>(in, B, C, H * W, Cp, out);
+    SMK_CHECK_LAUNCH();
+    return 0;
+}
+
+int conv1x1_sigmoid_nchw(const float* in, int B, int HW, int Cin, const float* w, const float* bias, int Cout, float* out,
+                         cudaStream_t st) {
+    SMK_REQUIRE(Cout <= 4 && Cin % 4 == 0, "conv1x1_sigmoid_nchw: Cout <= 4 and Cin %% 4 == 0 required");
+    size_t smem = (size_t)(Cin * Cout + Cout) * 4;
+    conv1x1_sigmoid_kernel<<<cdiv((long)B * HW, 256), 256, smem, st>>>(in, B, HW, Cin, w, bias, Cout, out);
+    SMK_CHECK_LAUNCH();
+    return 0;
+}
+
+int gap_linear(const float* feat, int B, int HW, int C, const float* w, const float* bias, int n_out, const uint8_t* codes,
+               float* out, cudaStream_t st) {
+    gap_linear_kernel<<<B, 256, (size_t)C * 4, st>>>(feat, HW, C, w, bias, n_out, codes, out);
+    SMK_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace smk

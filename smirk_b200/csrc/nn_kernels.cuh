@@ -1,0 +1,47 @@
+// fp32 CUDA-core building blocks shared by the encoder and the generator (NHWC activations).
+//
+// These are the exact-fp32 path (precision = 0): a tiled implicit-GEMM convolution with fused
+// BN / ReLU / residual / pixel-shuffle epilogues, depthwise 3x3, stem conv, 2x2 max-pool, layout
+// conversion, the final 1x1+sigmoid and the pooled linear heads.  The TF32 tcgen05 GEMM in
+// gemm_tc.cu replaces `conv_gemm` for the tensor-bound layers when precision = 1.
+#pragma once
+#include "common.cuh"
+
+namespace smk {
+
+// One convolution / GEMM problem:  C[m, n] = epi( sum_k A(m, k) * W[k, n] )
+//   m indexes output pixels (b, oh, ow) of an NHWC tensor, n output channels.
+//   mode 0: 1x1 conv / plain GEMM: A(m,k) = in[m*ld_in + k]
+//   mode 1: 3x3 stride-1 conv, zero padding 1:   k = (ky*3+kx)*Cin + c
+//   mode 2: 3x3 stride-1 conv, reflection padding 1
+struct ConvProblem {
+    const float* in; int ld_in;          // pixel stride of the input (>= Cin; lets us read a channel slice)
+    int B, H, W, Cin;                    // input spatial dims (= output dims: stride 1)
+    const float* w;                      // [K][N], n fastest
+    const float* scale; const float* bias;   // folded BN (or 1 / conv bias), per n
+    int N, K, mode;
+    int relu;
+    const float* res; int ld_res;        // optional residual added after scale/bias (no ReLU afterwards)
+    float* out; int ld_out;              // pixel stride of the output (>= N; lets us write a concat slice)
+    int shuffle;                         // 1: n = (dy*2+dx)*Cout + co  ->  pixel (2h+dy, 2w+dx), channel co
+};
+
+int conv_gemm(const ConvProblem& p, cudaStream_t st);
+
+// Depthwise 3x3, TF-"SAME" padding (pad_beg = pad_total/2), stride 1 or 2, fused scale/bias/ReLU.
+int dwconv3x3(const float* in, int B, int H, int W, int C, int stride, const float* w9c /*[9][C]*/,
+              const float* scale, const float* bias, float* out, cudaStream_t st);
+// Stem: NCHW fp32 image -> NHWC, 3x3 stride 2 TF-SAME, Cout = 16, fused scale/bias/ReLU.
+int stem_conv(const float* img_nchw, int B, int H, int W, const float* w /*[27][16]*/, const float* scale,
+              const float* bias, float* out, cudaStream_t st);
+int maxpool2x2(const float* in, int ld_in, int B, int H, int W, int C, float* out, cudaStream_t st);
+int nchw_to_nhwc_pad(const float* in, int B, int C, int H, int W, int Cp, float* out, cudaStream_t st);
+// out[b, co, h, w] = sigmoid(bias[co] + sum_c in[b,h,w,c] * w[c][co])   (NHWC -> NCHW)
+int conv1x1_sigmoid_nchw(const float* in, int B, int HW, int Cin, const float* w /*[Cin][Cout]*/, const float* bias,
+                         int Cout, float* out, cudaStream_t st);
+// Global average pool over HW pixels + Linear(C -> n_out); clamp codes per output column:
+//   0 none, 1 clamp[0,1], 2 relu, 3 clamp[-0.2,0.2]
+int gap_linear(const float* feat, int B, int HW, int C, const float* w /*[n_out][C]*/, const float* bias, int n_out,
+               const uint8_t* clamp_codes /*device, may be null*/, float* out, cudaStream_t st);
+
+}  // namespace smk

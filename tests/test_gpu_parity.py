@@ -1,0 +1,255 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI via the reference-signature modules,
+against the CPU oracle on the same seeded inputs, against the committed golden fixtures (outputs of
+the reference's own Python), and — at BASELINE.json's full batch sizes — through size-independent
+properties.  Tolerances: vertices / landmarks / rendered pixels 1e-4 relative (north_star); face
+indices and coverage bit-exact; encoder / generator in fp32 mode 1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+
+from smirk_b200 import synth_inputs
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+DEV = "cuda:0"
+
+
+def rel_close(a, b, rtol=1e-4, atol=0.0):
+    a = a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, np.float64)
+    b = b.detach().cpu().double().numpy() if torch.is_tensor(b) else np.asarray(b, np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = np.abs(a - b).max() if a.size else 0.0
+    ref = np.abs(b).max() if b.size else 0.0
+    assert err <= atol + rtol * ref, "max abs err %.3g vs ref max %.3g (rel %.3g)" % (err, ref, err / max(ref, 1e-30))
+    return err
+
+
+def cuda(d):
+    return {k: v.to(DEV) for k, v in d.items()}
+
+
+@pytest.fixture(scope="module")
+def mods(asset_root, native_lib):
+    import smirk_b200
+    assert torch.cuda.is_available(), "GPU suite needs a CUDA device"
+    return smirk_b200.FLAME().to(DEV), smirk_b200.Renderer().to(DEV)
+
+
+# ---------------------------------------------------------------------------------------------- FLAME
+def test_flame_vs_reference_golden(mods, golden):
+    fl, _ = mods
+    g = golden("flame")
+    o = fl.forward(cuda(synth_inputs.flame_params(4, 101)))
+    for k in ("vertices", "landmarks_fan", "landmarks_fan_3d", "landmarks_mp"):
+        rel_close(o[k], g["full/" + k])
+    p2 = synth_inputs.flame_params(2, 102)
+    short = {"shape_params": p2["shape_params"][:, :100], "expression_params": p2["expression_params"][:, :20],
+             "pose_params": p2["pose_params"], "jaw_params": p2["jaw_params"]}
+    o = fl.forward(cuda(short))                                    # padding + no-eyelid path (FLAME.py:244-248)
+    rel_close(o["vertices"], g["short/vertices"])
+    rel_close(o["landmarks_mp"], g["short/landmarks_mp"])
+    o = fl.forward(cuda(p2), zero_expression=True, zero_shape=True, zero_pose=True)
+    rel_close(o["vertices"], g["zero/vertices"])
+    rel_close(o["landmarks_fan"], g["zero/landmarks_fan"])
+
+
+def test_flame_contour_lut_sweep(mods, golden):
+    fl, _ = mods
+    ps = synth_inputs.flame_params(8, 103)
+    ps["pose_params"] = torch.tensor([[0.1, y, 0.05] for y in (-1.2, -0.69, -0.3, -0.01, 0.0, 0.2, 0.68, 1.3)])
+    o = fl.forward(cuda(ps))
+    rel_close(o["landmarks_fan"], golden("flame")["sweep/landmarks_fan"])
+
+
+def test_lbs_config1_and_joints(mods, golden, asset_root):
+    from oracle import flame_ref
+    fl, _ = mods
+    g = golden("flame")
+    p1 = synth_inputs.flame_params(1, 1001)
+    betas = torch.cat([p1["shape_params"], p1["expression_params"]], 1)
+    pose = torch.cat([p1["pose_params"], torch.zeros(1, 3), p1["jaw_params"], torch.zeros(1, 6)], 1)
+    r = fl.run_lbs(betas.to(DEV), pose.to(DEV), None)
+    rel_close(r["vertices"], g["c1/verts"])
+    rel_close(r["joints"], g["c1/joints"])
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 7, 32, 100])
+def test_flame_vs_oracle_batches(mods, asset_root, B):
+    from oracle import flame_ref
+    fl, _ = mods
+    c = flame_ref.FlameConstants(asset_root)
+    p = synth_inputs.flame_params(B, 2000 + B)
+    ref = flame_ref.flame_forward_ref(c, p)
+    o = fl.forward(cuda(p))
+    for k in ("vertices", "landmarks_fan", "landmarks_fan_3d", "landmarks_mp"):
+        rel_close(o[k], ref[k])
+    r = fl.run_lbs(torch.cat([p["shape_params"], p["expression_params"]], 1).to(DEV),
+                   torch.cat([p["pose_params"], torch.zeros(B, 3), p["jaw_params"], torch.zeros(B, 6)], 1).to(DEV),
+                   p["eyelid_params"].to(DEV))
+    assert torch.equal(r["dyn_idx"].cpu().long(), ref["_dyn_idx"])
+
+
+def test_flame_properties_full_batch(mods):
+    """B=256 (configs[2]): identity pose + zero betas returns the template; batch rows are independent."""
+    fl, _ = mods
+    B = 256
+    z = lambda n: torch.zeros(B, n, device=DEV)
+    o = fl.forward({"shape_params": z(300), "expression_params": z(50), "pose_params": z(3), "jaw_params": z(3)})
+    assert (o["vertices"] - fl.v_template[None]).abs().max() < 1e-6
+    p = cuda(synth_inputs.flame_params(B, 77))
+    a = fl.forward(p)["vertices"]
+    sub = {k: v[100:103] for k, v in p.items()}
+    b = fl.forward(sub)["vertices"]
+    rel_close(a[100:103], b, 1e-6)
+    assert fl.forward({k: v[:0] for k, v in p.items()})["vertices"].shape == (0, 5023, 3)     # empty batch
+
+
+# ------------------------------------------------------------------------------------------- Renderer
+def test_renderer_vs_reference_golden(mods, golden):
+    _, rd = mods
+    g = golden("render")
+    v, cam = T(g["vertices"]).to(DEV), T(g["cam"]).to(DEV)
+    lm_fan, lm_mp = v[:, :68].contiguous(), v[:, 100:205].contiguous()
+    o = rd.render_full(v, cam, landmarks_fan=lm_fan)
+    assert np.array_equal(o["pix_to_face"].cpu().numpy(), g["pix_to_face"].astype(np.int64))        # bit-exact
+    assert np.array_equal(o["bary"].cpu().numpy(), g["bary"])                                        # bit-exact
+    assert np.array_equal(o["transformed_vertices"].cpu().numpy(), g["transformed_vertices"])
+    rel_close(o["rendered_img"], g["rendered_img"])
+    out = rd.forward(v, cam, landmarks_fan=T(g["vertices"][:, :68]).to(DEV))
+    assert set(out) == {"rendered_img", "transformed_vertices", "landmarks_fan"} and out["landmarks_fan"].shape == (2, 68, 2)
+    assert torch.equal(out["rendered_img"], o["rendered_img"])
+
+
+@pytest.mark.parametrize("B,seed", [(1, 5), (5, 6), (32, 7)])
+def test_renderer_vs_oracle(mods, asset_root, B, seed):
+    from oracle import flame_ref, render_ref
+    _, rd = mods
+    c = flame_ref.FlameConstants(asset_root)
+    rc = render_ref.RenderConstants(asset_root)
+    p = synth_inputs.flame_params(B, 3000 + seed)
+    fo = flame_ref.flame_forward_ref(c, p)
+    ref = render_ref.render_forward_ref(rc, fo["vertices"], p["cam"], landmarks_fan=fo["landmarks_fan"],
+                                        landmarks_mp=fo["landmarks_mp"])
+    o = rd.render_full(fo["vertices"].to(DEV), p["cam"].to(DEV), landmarks_fan=fo["landmarks_fan"].to(DEV),
+                       landmarks_mp=fo["landmarks_mp"].to(DEV))
+    assert torch.equal(o["pix_to_face"].cpu(), ref["pix_to_face"]), \
+        "%d pixels differ" % int((o["pix_to_face"].cpu() != ref["pix_to_face"]).sum())
+    assert torch.equal(o["bary"].cpu(), ref["bary"])
+    assert torch.equal(o["zbuf"].cpu(), ref["zbuf"])
+    assert torch.equal(o["transformed_vertices"].cpu(), ref["transformed_vertices"])
+    rel_close(o["normals"], ref["normals"], 1e-5, 1e-6)
+    rel_close(o["rendered_img"], ref["rendered_img"])
+    for k in ("landmarks_fan", "landmarks_mp"):
+        assert torch.equal(o[k].cpu(), ref[k])
+
+
+def test_renderer_edge_cases(mods, asset_root):
+    from oracle import render_ref
+    _, rd = mods
+    rc = render_ref.RenderConstants(asset_root)
+    base = T(np.load(asset_root + "/assets/l_eyelid.npy")).float() * 0        # [5023,3] zeros
+    tmpl = torch.tensor(np.array([[float(x) for x in ln.split()[1:4]] for ln in open(asset_root + "/assets/head_template.obj")
+                                  if ln.startswith("v ")], dtype=np.float32))
+    tmpl = tmpl - tmpl.mean(0)
+    verts = torch.stack([tmpl, base, tmpl, tmpl])                  # row 1: fully degenerate mesh (all zero-area)
+    cam = torch.tensor([[7.0, 0, 0], [7.0, 0, 0], [60.0, 0.0, 0.0], [7.0, 3.0, -3.0]])   # zoomed-in; shifted off-screen
+    ref = render_ref.render_forward_ref(rc, verts, cam)
+    o = rd.render_full(verts.to(DEV), cam.to(DEV))
+    assert torch.equal(o["pix_to_face"].cpu(), ref["pix_to_face"])
+    assert (o["pix_to_face"][1] == -1).all() and (o["rendered_img"][1] == 0).all()
+    assert (o["pix_to_face"][3] == -1).all()
+    assert (o["pix_to_face"][2] >= 0).float().mean() > 0.5
+    rel_close(o["rendered_img"], ref["rendered_img"])
+    e = rd.forward(verts[:0].to(DEV), cam[:0].to(DEV))
+    assert e["rendered_img"].shape == (0, 3, 224, 224)
+
+
+def test_renderer_properties_full_batch(mods):
+    """B=256: per-image independence, background exactly 0, grey image (3 equal channels),
+    packed indices lie in their own image's range, barycentrics sum to 1."""
+    fl, rd = mods
+    B = 256
+    p = cuda(synth_inputs.flame_params(B, 88))
+    v = fl.forward(p)["vertices"]
+    o = rd.render_full(v, p["cam"])
+    img, p2f = o["rendered_img"], o["pix_to_face"]
+    assert torch.equal(img[:, 0], img[:, 1]) and torch.equal(img[:, 0], img[:, 2])
+    assert (img[:, 0][p2f < 0] == 0).all() and float(img.max()) <= 1.7 * 180 / 255 + 1e-5
+    lo = torch.arange(B, device=DEV).view(B, 1, 1) * 3408
+    ok = (p2f < 0) | ((p2f >= lo) & (p2f < lo + 3408))
+    assert ok.all()
+    s = o["bary"].sum(-1)[p2f >= 0]
+    assert (s - 1).abs().max() < 1e-4
+    o2 = rd.render_full(v[17:19].contiguous(), p["cam"][17:19].contiguous())
+    assert torch.equal(o2["rendered_img"], img[17:19])
+    assert torch.equal(o2["pix_to_face"] + 17 * 3408 * (o2["pix_to_face"] >= 0), p2f[17:19])
+
+
+# -------------------------------------------------------------------------------------------- Encoder
+@pytest.fixture(scope="module")
+def encoder(native_lib):
+    import smirk_b200
+    enc = smirk_b200.SmirkEncoder()
+    enc.load_state_dict(synth_inputs.random_state_dict(enc.state_dict(), seed=7))
+    return enc.eval().to(DEV)
+
+
+def test_encoder_vs_golden_and_oracle(encoder, golden):
+    from oracle import encoder_ref
+    g = golden("encoder")
+    o = encoder(synth_inputs.images(2, 401).to(DEV))
+    assert set(o) == {"pose_params", "cam", "shape_params", "expression_params", "eyelid_params", "jaw_params"}
+    for k in o:
+        rel_close(o[k], g[k], 1e-4, 1e-5)
+    img = synth_inputs.images(5, 402)
+    ref = encoder_ref.encoder_forward_ref({k: v.cpu() for k, v in encoder.state_dict().items()}, img)
+    o = encoder(img.to(DEV))
+    for k in o:
+        rel_close(o[k], ref[k], 1e-4, 1e-5)
+    assert o["shape_params"].shape == (5, 300) and o["cam"].shape == (5, 3)
+
+
+def test_encoder_repack_on_weight_change_and_properties(encoder):
+    img = synth_inputs.images(32, 403).to(DEV)
+    a = encoder(img)
+    b = encoder(img[5:9].contiguous())
+    for k in a:
+        rel_close(b[k], a[k][5:9], 1e-5, 1e-6)                     # batch rows independent
+    import copy
+    e2 = copy.deepcopy(encoder)
+    with torch.no_grad():
+        e2.shape_encoder.shape_layers[0].bias += 1.0
+    c = e2(img[:2].contiguous())
+    rel_close(c["shape_params"], a["shape_params"][:2] + 1.0, 1e-5, 1e-5)
+    assert (a["eyelid_params"] >= 0).all() and (a["eyelid_params"] <= 1).all()
+    assert (a["jaw_params"][:, 0] >= 0).all() and (a["jaw_params"][:, 1:].abs() <= 0.2).all()
+
+
+# ------------------------------------------------------------------------------------------ Generator
+@pytest.fixture(scope="module")
+def generator(native_lib):
+    import smirk_b200
+    gen = smirk_b200.SmirkGenerator(in_channels=6, out_channels=3, init_features=32, res_blocks=5)
+    gen.load_state_dict(synth_inputs.random_state_dict(gen.state_dict(), seed=7))
+    return gen.eval().to(DEV)
+
+
+def test_generator_vs_golden_and_oracle(generator, golden):
+    from oracle import generator_ref
+    g, r = golden("generator"), golden("render")
+    x = torch.cat([T(r["rendered_img"][:1]), synth_inputs.masked_images(1, 301)], 1)
+    y = generator(x.to(DEV))
+    rel_close(y[:, :, ::4, ::4], g["y_sub"], 1e-4, 1e-5)
+    rel_close(y[:, :, 100:102], g["y_rows"], 1e-4, 1e-5)
+    x2 = torch.cat([T(r["rendered_img"]), synth_inputs.masked_images(2, 302)], 1)
+    ref = generator_ref.generator_forward_ref({k: v.cpu() for k, v in generator.state_dict().items()}, x2)
+    y2 = generator(x2.to(DEV))
+    rel_close(y2, ref, 1e-4, 1e-5)
+    assert y2.shape == (2, 3, 224, 224) and float(y2.min()) > 0 and float(y2.max()) < 1
+
+
+def test_generator_batch_independence(generator):
+    x = torch.cat([synth_inputs.images(8, 303), synth_inputs.masked_images(8, 304)], 1).to(DEV)
+    a = generator(x)
+    b = generator(x[3:5].contiguous())
+    rel_close(b, a[3:5], 1e-5, 1e-6)
