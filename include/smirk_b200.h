@@ -31,6 +31,16 @@ extern "C" {
 int smk_version(void);
 const char* smk_last_error(void);
 
+/* Launch accounting and the built-in event profiler (used by bench.py for `gpu_launches` and the
+ * per-kernel roofline): smk_launch_count() = kernels launched by this library so far in the process;
+ * with the profiler enabled every launch is bracketed by CUDA events on its own stream (do not enable
+ * during CUDA-graph capture).  smk_profiler_report writes "tag launches total_ms bytes flops" lines
+ * (algorithmic bytes / FLOPs summed over launches), returns the number of lines or -1 if buf is small. */
+unsigned long long smk_launch_count(void);
+void smk_profiler_enable(int on);
+void smk_profiler_reset(void);
+int smk_profiler_report(char* buf, size_t n);
+
 /* ------------------------------------------------------------------------------------------------
  * FLAME  — replaces FLAME.forward (src/FLAME/FLAME.py:232-315) and lbs() (src/FLAME/lbs.py:140-227).
  * ---------------------------------------------------------------------------------------------- */

@@ -44,7 +44,8 @@ class SmkGeneratorDesc(C.Structure):
                 ("precision", C.c_int)]
 
 
-SYMBOLS = ["smk_version", "smk_last_error",
+SYMBOLS = ["smk_version", "smk_last_error", "smk_launch_count", "smk_profiler_enable", "smk_profiler_reset",
+           "smk_profiler_report",
            "smk_flame_create", "smk_flame_destroy", "smk_flame_workspace_bytes", "smk_flame_forward",
            "smk_renderer_create", "smk_renderer_destroy", "smk_renderer_workspace_bytes", "smk_renderer_forward",
            "smk_project_points",
@@ -69,6 +70,11 @@ def lib():
         elif name.endswith("_destroy"):
             fn.restype = None
     vp, i, sz = C.c_void_p, C.c_int, C.c_size_t
+    L.smk_launch_count.restype = C.c_ulonglong
+    L.smk_profiler_enable.argtypes = [i]
+    L.smk_profiler_enable.restype = None
+    L.smk_profiler_reset.restype = None
+    L.smk_profiler_report.argtypes = [C.c_char_p, sz]
     L.smk_flame_create.argtypes = [C.POINTER(SmkFlameDesc), C.POINTER(vp)]
     L.smk_flame_destroy.argtypes = [vp]
     L.smk_flame_workspace_bytes.argtypes = [vp, i]
@@ -141,3 +147,16 @@ class Workspace:
         if self.buf is None or self.buf.device != device or self.buf.numel() < nbytes:
             self.buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         return self.buf
+
+
+def profiler_report():
+    """-> {tag: dict(launches, ms, bytes, flops)} accumulated since the last reset."""
+    buf = C.create_string_buffer(1 << 16)
+    n = lib().smk_profiler_report(buf, len(buf))
+    if n < 0:
+        raise RuntimeError("smirk_b200: profiler report buffer too small")
+    out = {}
+    for ln in buf.value.decode().splitlines():
+        tag, launches, ms, by, fl = ln.split()
+        out[tag] = dict(launches=int(launches), ms=float(ms), bytes=float(by), flops=float(fl))
+    return out

@@ -25,7 +25,14 @@ void set_error(const char* fmt, ...);
         if (!(cond)) { smk::set_error(__VA_ARGS__); return -1; }                        \
     } while (0)
 
-#define SMK_CHECK_LAUNCH() SMK_CHECK_CUDA(cudaGetLastError())
+// Launch bookkeeping: every kernel launch site calls SMK_TAG(...) first.  It counts launches (the
+// `gpu_launches` figure bench.py reports) and, when the built-in profiler is enabled
+// (smk_profiler_enable), brackets the launch with CUDA events on the launching stream so bench.py can
+// report per-kernel time, algorithmic bytes and FLOPs without an external profiler.
+void prof_begin(const char* tag, double bytes, double flops, cudaStream_t st);
+void prof_end();
+#define SMK_TAG(tag, bytes, flops, st) smk::prof_begin(tag, (double)(bytes), (double)(flops), st)
+#define SMK_CHECK_LAUNCH() do { smk::prof_end(); SMK_CHECK_CUDA(cudaGetLastError()); } while (0)
 
 // Device buffers owned by a handle (constants only; forwards never allocate).
 struct DeviceArena {

@@ -167,8 +167,8 @@ static int pointwise(const ConvW& c, const float* in, int B, int H, int W, bool 
 
 extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B, float* pose_cam, float* shape,
                                    float* expr, void* ws, size_t ws_bytes, void* stream) {
+    if (B == 0) return 0;                      // empty batch: nothing to do (pointers may be null)
     SMK_REQUIRE(h && img && pose_cam && shape && expr, "smk_encoder_forward: null argument");
-    if (B == 0) return 0;
     SMK_REQUIRE(B > 0, "smk_encoder_forward: negative batch");
     SMK_REQUIRE(ws && ws_bytes >= smk_encoder_workspace_bytes(h, B), "smk_encoder_forward: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;

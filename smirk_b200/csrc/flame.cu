@@ -333,6 +333,8 @@ static int launch_verts(const FlameDev& d, const float* betas, const float* eyel
     if (smem > 48 * 1024)
         SMK_CHECK_CUDA(cudaFuncSetAttribute(flame_verts_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(smk::cdiv(d.V, 128), smk::cdiv(B, BT));
+    SMK_TAG("flame_verts", 4.0 * ((double)(d.L + kPF) * d.Mp + 6.0 * d.Mp + 5.0 * d.V + (double)B * (d.L + 3.0 * d.V + 98)),
+            2.0 * B * (3.0 * d.V * (d.L + kPF) + (double)d.V * (60 + 12 + 6)), st);
     flame_verts_kernel<BT><<<grid, 128, smem, st>>>(d, betas, eyelid, A, pf, B, verts);
     SMK_CHECK_LAUNCH();
     return 0;
@@ -341,8 +343,8 @@ static int launch_verts(const FlameDev& d, const float* betas, const float* eyel
 extern "C" int smk_flame_forward(const SmkFlame* h, const float* betas, const float* full_pose, const float* eyelid,
                                  int B, float* verts, float* lmk_fan, float* lmk_fan3d, float* lmk_mp,
                                  float* joints, int32_t* dyn_idx, void* ws, size_t ws_bytes, void* stream) {
+    if (B == 0) return 0;                      // empty batch: nothing to do (pointers may be null)
     SMK_REQUIRE(h && betas && full_pose && verts && lmk_fan && lmk_fan3d && lmk_mp, "smk_flame_forward: null argument");
-    if (B == 0) return 0;
     SMK_REQUIRE(B > 0, "smk_flame_forward: negative batch");
     SMK_REQUIRE(ws && ws_bytes >= smk_flame_workspace_bytes(h, B), "smk_flame_forward: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
@@ -351,6 +353,7 @@ extern "C" int smk_flame_forward(const SmkFlame* h, const float* betas, const fl
     float* pf = w.take<float>((size_t)B * kPF);
     int32_t* dyn = w.take<int32_t>(B);
     const FlameDev& d = h->d;
+    SMK_TAG("flame_pose", 4.0 * (15.0 * d.L + (double)B * (d.L + 15 + 60 + kPF + 16)), 2.0 * B * 15.0 * d.L, st);
     flame_pose_kernel<<<B, 128, 0, st>>>(d, betas, full_pose, B, A, pf, joints, dyn);
     SMK_CHECK_LAUNCH();
     int rc;
@@ -359,6 +362,7 @@ extern "C" int smk_flame_forward(const SmkFlame* h, const float* betas, const fl
     else if (B >= 2) rc = launch_verts<2>(d, betas, eyelid, A, pf, B, verts, st);
     else rc = launch_verts<1>(d, betas, eyelid, A, pf, B, verts, st);
     if (rc) return rc;
+    SMK_TAG("flame_landmarks", 4.0 * B * 241.0 * (9 + 3 + 3 + 4), 2.0 * B * 241 * 9, st);
     flame_landmarks_kernel<<<B, 256, 0, st>>>(d, verts, dyn, B, lmk_fan, lmk_fan3d, lmk_mp);
     SMK_CHECK_LAUNCH();
     if (dyn_idx) SMK_CHECK_CUDA(cudaMemcpyAsync(dyn_idx, dyn, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));

@@ -156,8 +156,8 @@ static int conv3(const Conv3& c, const float* in, int ld_in, int B, int S, int m
 
 extern "C" int smk_generator_forward(const SmkGenerator* h, const float* x, int B, float* y,
                                      void* ws, size_t ws_bytes, void* stream) {
+    if (B == 0) return 0;                      // empty batch: nothing to do (pointers may be null)
     SMK_REQUIRE(h && x && y, "smk_generator_forward: null argument");
-    if (B == 0) return 0;
     SMK_REQUIRE(B > 0, "smk_generator_forward: negative batch");
     SMK_REQUIRE(ws && ws_bytes >= smk_generator_workspace_bytes(h, B), "smk_generator_forward: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;

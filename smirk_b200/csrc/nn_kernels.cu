@@ -298,6 +298,12 @@ int conv_gemm(const ConvProblem& p, cudaStream_t st) {
     const int M = p.B * p.H * p.W;
     SMK_REQUIRE(p.K % 4 == 0 && p.N % 4 == 0 && p.ld_in % 4 == 0, "conv_gemm: K, N, ld_in must be multiples of 4");
     SMK_REQUIRE(p.mode == 0 || p.Cin % 4 == 0, "conv_gemm: Cin must be a multiple of 4");
+    {
+        const double cin_eff = p.mode == 0 ? p.K : p.Cin;       // unique input bytes (not im2col-expanded)
+        SMK_TAG(p.mode == 0 ? (p.shuffle ? "upconv_gemm_f32" : "pw_gemm_f32") : "conv3x3_gemm_f32",
+                4.0 * ((double)M * cin_eff + (double)p.K * p.N + (double)M * p.N * (p.res ? 2 : 1) + 2.0 * p.N),
+                2.0 * (double)M * p.N * p.K, st);
+    }
     if (p.N <= 32) {
         dim3 grid(cdiv(M, 128), cdiv(p.N, 32));
         conv_gemm_kernel<128, 32><<<grid, NT, 0, st>>>(p, M);
@@ -322,6 +328,7 @@ int dwconv3x3(const float* in, int B, int H, int W, int C, int stride, const flo
     int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
     long total = (long)B * Ho * Wo * (C / 4);
     int blocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
+    SMK_TAG("dwconv3x3", 4.0 * ((double)B * H * W * C + (double)B * Ho * Wo * C + 11.0 * C), 18.0 * B * Ho * Wo * C, st);
     dwconv3x3_kernel<<<blocks, 256, 0, st>>>(in, B, H, W, C, stride, same_pad_begin(H, stride), Ho, Wo, w9c, scale, bias, out);
     SMK_CHECK_LAUNCH();
     return 0;
@@ -330,6 +337,7 @@ int dwconv3x3(const float* in, int B, int H, int W, int C, int stride, const flo
 int stem_conv(const float* img, int B, int H, int W, const float* w, const float* scale, const float* bias, float* out,
               cudaStream_t st) {
     int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    SMK_TAG("stem_conv", 4.0 * ((double)B * 3 * H * W + (double)B * Ho * Wo * 16 + 27 * 16 + 32), 2.0 * 27 * 16 * (double)B * Ho * Wo, st);
     stem_conv_kernel<<<cdiv((long)B * Ho * Wo, 128), 128, 0, st>>>(img, B, H, W, Ho, Wo, same_pad_begin(H, 2), w, scale, bias, out);
     SMK_CHECK_LAUNCH();
     return 0;
@@ -338,12 +346,14 @@ int stem_conv(const float* img, int B, int H, int W, const float* w, const float
 int maxpool2x2(const float* in, int ld_in, int B, int H, int W, int C, float* out, cudaStream_t st) {
     long total = (long)B * (H / 2) * (W / 2) * (C / 4);
     int blocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
+    SMK_TAG("maxpool2x2", 4.0 * 1.25 * (double)B * H * W * C, 0.0, st);
     maxpool2x2_kernel<<<blocks, 256, 0, st>>>(in, ld_in, B, H, W, C, out);
     SMK_CHECK_LAUNCH();
     return 0;
 }
 
 int nchw_to_nhwc_pad(const float* in, int B, int C, int H, int W, int Cp, float* out, cudaStream_t st) {
+    SMK_TAG("nchw_to_nhwc", 4.0 * (double)B * H * W * (C + Cp), 0.0, st);
     nchw_to_nhwc_pad_kernel<<<cdiv((long)B * H * W, 256), 256, 0, st>>>(in, B, C, H * W, Cp, out);
     SMK_CHECK_LAUNCH();
     return 0;
@@ -353,6 +363,7 @@ int conv1x1_sigmoid_nchw(const float* in, int B, int HW, int Cin, const float* w
                          cudaStream_t st) {
     SMK_REQUIRE(Cout <= 4 && Cin % 4 == 0, "conv1x1_sigmoid_nchw: Cout <= 4 and Cin %% 4 == 0 required");
     size_t smem = (size_t)(Cin * Cout + Cout) * 4;
+    SMK_TAG("conv1x1_sigmoid", 4.0 * (double)B * HW * (Cin + Cout), 2.0 * (double)B * HW * Cin * Cout, st);
     conv1x1_sigmoid_kernel<<<cdiv((long)B * HW, 256), 256, smem, st>>>(in, B, HW, Cin, w, bias, Cout, out);
     SMK_CHECK_LAUNCH();
     return 0;
@@ -360,6 +371,7 @@ int conv1x1_sigmoid_nchw(const float* in, int B, int HW, int Cin, const float* w
 
 int gap_linear(const float* feat, int B, int HW, int C, const float* w, const float* bias, int n_out, const uint8_t* codes,
                float* out, cudaStream_t st) {
+    SMK_TAG("gap_linear", 4.0 * ((double)B * HW * C + (double)n_out * C + (double)B * n_out), 2.0 * (double)B * C * (HW + n_out), st);
     gap_linear_kernel<<<B, 256, (size_t)C * 4, st>>>(feat, HW, C, w, bias, n_out, codes, out);
     SMK_CHECK_LAUNCH();
     return 0;

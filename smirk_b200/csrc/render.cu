@@ -284,6 +284,7 @@ extern "C" size_t smk_renderer_workspace_bytes(const SmkRenderer* h, int B) {
 extern "C" int smk_project_points(const float* pts, const float* cam, int B, int L, float* out_xy, void* stream) {
     SMK_REQUIRE(pts && cam && out_xy, "smk_project_points: null argument");
     if (B <= 0 || L <= 0) return 0;
+    SMK_TAG("project_points", 4.0 * B * (5.0 * L + 3), 4.0 * B * L, (cudaStream_t)stream);
     project_kernel<<<smk::cdiv((long)B * L, 256), 256, 0, (cudaStream_t)stream>>>(pts, cam, B, L, 2, out_xy);
     SMK_CHECK_LAUNCH();
     return 0;
@@ -292,8 +293,8 @@ extern "C" int smk_project_points(const float* pts, const float* cam, int B, int
 extern "C" int smk_renderer_forward(const SmkRenderer* h, const float* verts, const float* cam, int B,
                                     float* rendered, float* tverts, int64_t* pix_to_face, float* bary, float* zbuf,
                                     float* normals_out, void* ws, size_t ws_bytes, void* stream) {
+    if (B == 0) return 0;                      // empty batch: nothing to do (pointers may be null)
     SMK_REQUIRE(h && verts && cam && rendered && tverts, "smk_renderer_forward: null argument");
-    if (B == 0) return 0;
     SMK_REQUIRE(B > 0, "smk_renderer_forward: negative batch");
     SMK_REQUIRE(ws && ws_bytes >= smk_renderer_workspace_bytes(h, B), "smk_renderer_forward: workspace too small");
     const RenderDev& d = h->d;
@@ -304,14 +305,18 @@ extern "C" int smk_renderer_forward(const SmkRenderer* h, const float* verts, co
     float* recs = w.take<float>((size_t)B * d.F * REC);
     uint32_t* ranges = w.take<uint32_t>((size_t)B * d.F);
     float* nrm = normals_out ? normals_out : nrm_ws;
+    SMK_TAG("project_verts", 4.0 * B * (6.0 * d.V + 3), 5.0 * B * d.V, st);
     project_kernel<<<smk::cdiv((long)B * d.V, 256), 256, 0, st>>>(verts, cam, B, d.V, 3, tverts);
     SMK_CHECK_LAUNCH();
+    SMK_TAG("submesh_normals", 4.0 * B * (9.0 * d.NM) + 4.0 * (4.0 * d.F + 2.0 * d.NM), 30.0 * B * 3.0 * d.F, st);
     submesh_kernel<<<dim3(smk::cdiv(d.NM, 128), B), 128, 0, st>>>(d, verts, tverts, B, rv, nrm);
     SMK_CHECK_LAUNCH();
+    SMK_TAG("tri_setup", 4.0 * B * (3.0 * d.NM + (double)d.F * (REC + 1)) + 12.0 * d.F, 40.0 * B * d.F, st);
     tri_setup_kernel<<<dim3(smk::cdiv(d.F, 128), B), 128, 0, st>>>(d, rv, B, recs, ranges);
     SMK_CHECK_LAUNCH();
     size_t smem = (size_t)CHUNK * REC * 4 + (((size_t)d.F * 2 + 15) & ~size_t(15));
     dim3 grid(d.S / TILE_W, d.S / TILE_H, B);
+    SMK_TAG("raster_tile", 4.0 * B * ((double)d.F * (REC + 1) + 3.0 * d.NM + (double)d.S * d.S * (3 + (pix_to_face ? 2 : 0) + (bary ? 3 : 0) + (zbuf ? 1 : 0))), 0.0, st);
     raster_tile_kernel<<<grid, dim3(TILE_W, TILE_H), smem, st>>>(d, recs, ranges, nrm, h->lights, B, rendered, pix_to_face, bary, zbuf);
     SMK_CHECK_LAUNCH();
     return 0;
