@@ -181,6 +181,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel breakdown JSON here")
     args = ap.parse_args()
+    if args.profile_out:
+        args.profile_out = os.path.abspath(args.profile_out)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -153,6 +153,23 @@ size_t smk_generator_workspace_bytes(const SmkGenerator* h, int B);
 int smk_generator_forward(const SmkGenerator* h, const float* x, int B, float* y,
                           void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Kernel-level test entry points (used by tests/ to check single convolution kernels against torch;
+ * not part of the drop-in surface).  All pointers are device pointers.
+ *   smk_debug_conv_f32: fp32 CUDA-core implicit GEMM.  w_kn is [K][N]; mode 0 = 1x1, 1 = 3x3 zero pad,
+ *                       2 = 3x3 reflection pad; shuffle = 1 stores ConvTranspose2d(k2,s2) pixel-shuffled.
+ *   smk_debug_conv_tc : TF32 tcgen05 implicit GEMM.  wt is [N][K]; mode 2 expects `in` to be a
+ *                       [B,H+2,W+2,*] buffer whose halo was filled by smk_debug_reflect_halo;
+ *                       store 0 plain, 1 pixel-shuffle, 2 interior of a padded [B,H+2,W+2,*] buffer.
+ * ---------------------------------------------------------------------------------------------- */
+int smk_debug_conv_f32(const float* in, int ld_in, int B, int H, int W, int Cin, const float* w_kn, const float* scale,
+                       const float* bias, int N, int K, int mode, int relu, const float* res, int ld_res,
+                       float* out, int ld_out, int shuffle, void* stream);
+int smk_debug_conv_tc(const float* in, int ld_in, int B, int H, int W, int Cin, const float* wt, const float* scale,
+                      const float* bias, int N, int K, int mode, int relu, const float* res, int ld_res, int res_pad,
+                      float* out, int ld_out, int store, void* stream);
+int smk_debug_reflect_halo(float* buf, int B, int H, int W, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

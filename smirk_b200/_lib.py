@@ -50,7 +50,8 @@ SYMBOLS = ["smk_version", "smk_last_error", "smk_launch_count", "smk_profiler_en
            "smk_renderer_create", "smk_renderer_destroy", "smk_renderer_workspace_bytes", "smk_renderer_forward",
            "smk_project_points",
            "smk_encoder_create", "smk_encoder_destroy", "smk_encoder_workspace_bytes", "smk_encoder_forward",
-           "smk_generator_create", "smk_generator_destroy", "smk_generator_workspace_bytes", "smk_generator_forward"]
+           "smk_generator_create", "smk_generator_destroy", "smk_generator_workspace_bytes", "smk_generator_forward",
+           "smk_debug_conv_f32", "smk_debug_conv_tc", "smk_debug_reflect_halo"]
 
 
 def lib():
@@ -92,6 +93,9 @@ def lib():
     L.smk_generator_destroy.argtypes = [vp]
     L.smk_generator_workspace_bytes.argtypes = [vp, i]
     L.smk_generator_forward.argtypes = [vp, vp, i, vp, vp, sz, vp]
+    L.smk_debug_conv_f32.argtypes = [vp, i, i, i, i, i, vp, vp, vp, i, i, i, i, vp, i, vp, i, i, vp]
+    L.smk_debug_conv_tc.argtypes = [vp, i, i, i, i, i, vp, vp, vp, i, i, i, i, vp, i, i, vp, i, i, vp]
+    L.smk_debug_reflect_halo.argtypes = [vp, i, i, i, i, vp]
     if L.smk_version() != 100:
         raise RuntimeError("smirk_b200: library/header version mismatch (%d)" % L.smk_version())
     _lib = L

@@ -1,0 +1,401 @@
+// TF32 tcgen05 implicit-GEMM convolution for sm_100a:  C[M,N] = epi( A[M,K] * W[N,K]^T ).
+//
+// This is the tensor-core path of the generator's 3x3 convolutions / transposed convolutions and of
+// the encoder's 1x1 convolutions (precision = 1).  The reference executes these layers as cuDNN
+// TF32 implicit GEMMs (src/smirk_generator.py:56-76,147-178; torch default cudnn.allow_tf32=True);
+// here they are one hand-written kernel:
+//
+//   * A (activations, NHWC fp32) is fetched tile-by-tile by TMA: `cp.async.bulk.tensor.2d` for 1x1
+//     convs / plain GEMMs, `cp.async.bulk.tensor.4d...im2col` for 3x3 convs — the hardware walks 128
+//     consecutive output pixels (crossing rows and images), applies the filter-tap offset and zero
+//     fills the padding halo, writing a 128 x 32-channel (128-byte rows) SWIZZLE_128B tile into
+//     shared memory.  No im2col matrix is ever materialised.
+//   * W ([N][K], K-major, K ordered (tap, channel)) comes in through a 2-D TMA box of BN x 32.
+//   * One elected thread issues `tcgen05.mma.cta_group::1.kind::tf32` (M=128, N=BN, K=8 per
+//     instruction, 4 per 128-byte k-block); the fp32 accumulator lives in TMEM (BN columns).
+//   * A STAGES-deep mbarrier ring decouples the TMA producer warp from the MMA warp;
+//     `tcgen05.commit` releases shared-memory stages and finally signals the epilogue warps, which
+//     read the accumulator with `tcgen05.ld.32x32b`, apply folded BatchNorm scale/bias, optional
+//     residual and ReLU, and store NHWC rows — plain, into a channel slice of a concat buffer, into
+//     the interior of a reflection-padded buffer, or pixel-shuffled (ConvTranspose2d k2 s2).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (warp_id % 4 selects the TMEM lane quarter each may access).
+#include "gemm_tc.cuh"
+#include <cuda.h>
+
+namespace smk {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BKB = 128;                  // bytes of K per k-block = one SWIZZLE_128B row = 32 fp32
+constexpr int BK = 32;
+constexpr int UMMA_K = 8;                 // tf32
+constexpr int A_STAGE_BYTES = BM * BKB;   // 16 KiB
+constexpr int NUM_THREADS = 192;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col(const CUtensorMap* map, void* dst, uint64_t* bar, int c, int w, int h, int n,
+                                                uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (= 1, unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (= 1024 B between 8-row groups) | [46,48) version = 1 | [61,64) layout = 2
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=TF32 [7,10)=2, b=TF32 [10,13)=2,
+// K-major A/B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcArgs {
+    int M, N, nkb;                 // nkb = number of 32-wide k-blocks
+    int mode;                      // 0 = 2-D tiled A; 1 = im2col A
+    int H, W;                      // output spatial dims (im2col tile origin decode; shuffle / padded stores)
+    int cpb;                       // k-blocks per filter tap (Cin / 32) for im2col
+    int lc;                        // im2col lower corner (-1: zero padding 1; 0: input already reflection-padded)
+    const float* scale; const float* bias;
+    const float* res; int ld_res; int res_pad;   // residual (optionally read from the interior of a padded buffer)
+    int relu;
+    float* out; int ld_out;
+    int store;                     // 0 plain, 1 pixel-shuffle (N = 4*Cout), 2 interior of a (H+2)x(W+2) padded buffer
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+    constexpr int B_STAGE_BYTES = BN * BKB;
+    constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t IDESC = make_idesc(BM, BN);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int q0 = 0, p0 = 0, img = 0;
+            if (a.mode == 1) { int hw = a.H * a.W; img = m0 / hw; int r = m0 - img * hw; p0 = r / a.W; q0 = r - p0 * a.W; }
+            for (int kb = 0; kb < a.nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                uint8_t* sa = smem + s * STAGE_BYTES;
+                uint8_t* sb = sa + A_STAGE_BYTES;
+                mbar_expect_tx(&full[s], (uint32_t)STAGE_BYTES);
+                if (a.mode == 0) {
+                    tma_load_2d(&tmA, sa, &full[s], kb * BK, m0);
+                } else {
+                    int tap = kb / a.cpb, ch = kb - tap * a.cpb;
+                    int r = tap / 3, sx = tap - r * 3;
+                    tma_load_im2col(&tmA, sa, &full[s], ch * BK, q0 + a.lc, p0 + a.lc, img, (uint16_t)sx, (uint16_t)r);
+                }
+                tma_load_2d(&tmB, sb, &full[s], kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            for (int kb = 0; kb < a.nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(&full[s], ph);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    uint64_t da = make_smem_desc(sa + k * UMMA_K * 4);
+                    uint64_t db = make_smem_desc(sb + k * UMMA_K * 4);
+                    umma_tf32(tmem_base, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+                }
+                tcgen05_commit(&empty[s]);          // frees this smem stage once the MMAs above have read it
+            }
+            tcgen05_commit(tmem_full);              // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        mbar_wait(tmem_full, 0);
+        tcgen05_fence_after();
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int m = m0 + row;
+        const bool row_ok = m < a.M;
+        size_t out_pix = (size_t)(row_ok ? m : 0), res_pix = out_pix;
+        int b = 0, h = 0, w = 0;
+        if (a.store != 0 || a.res_pad) {
+            int hw = a.H * a.W; int mm = row_ok ? m : 0;
+            b = mm / hw; int r = mm - b * hw; h = r / a.W; w = r - h * a.W;
+            size_t padded = ((size_t)b * (a.H + 2) + h + 1) * (a.W + 2) + w + 1;
+            if (a.store == 2) out_pix = padded;
+            if (a.res_pad) res_pix = padded;
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);     // warp-collective
+            const int n = n0 + c0;
+            if (!row_ok || n >= a.N) continue;
+            const int nv = min(32, a.N - n);
+            float* dst;
+            if (a.store == 1) {                      // ConvTranspose2d k2 s2: n = (dy*2+dx)*Cout + co
+                int cout = a.N >> 2, q = n / cout, co = n - q * cout;
+                size_t dp = ((size_t)b * (2 * a.H) + 2 * h + (q >> 1)) * (2 * a.W) + 2 * w + (q & 1);
+                dst = a.out + dp * a.ld_out + co;
+            } else {
+                dst = a.out + out_pix * a.ld_out + n;
+            }
+            const float* rs = a.res ? a.res + res_pix * a.ld_res + n : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                if (j >= nv) break;
+                float4 sc = *reinterpret_cast<const float4*>(a.scale + n + j);
+                float4 bi = *reinterpret_cast<const float4*>(a.bias + n + j);
+                float4 o;
+                o.x = fmaf(v[j], sc.x, bi.x); o.y = fmaf(v[j + 1], sc.y, bi.y);
+                o.z = fmaf(v[j + 2], sc.z, bi.z); o.w = fmaf(v[j + 3], sc.w, bi.w);
+                if (rs) { float4 r4 = *reinterpret_cast<const float4*>(rs + j); o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
+                if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                *reinterpret_cast<float4*>(dst + j) = o;
+            }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- reflection halo of a [B, H+2, W+2, C] buffer whose interior has been written -------------------
+__global__ void __launch_bounds__(256)
+reflect_halo_kernel(float* __restrict__ buf, int B, int H, int W, int C) {
+    const int Hp = H + 2, Wp = W + 2, C4 = C >> 2;
+    const int halo = 2 * Wp + 2 * H;                       // halo pixels per image
+    long total = (long)B * halo * C4;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int c4 = (int)(i % C4); long t = i / C4; int k = (int)(t % halo); int b = (int)(t / halo);
+        int ph, pw;
+        if (k < Wp) { ph = 0; pw = k; }
+        else if (k < 2 * Wp) { ph = Hp - 1; pw = k - Wp; }
+        else { int r = k - 2 * Wp; ph = 1 + (r >> 1); pw = (r & 1) ? Wp - 1 : 0; }
+        // ReflectionPad2d(1): padded index p -> interior index |p-1| mirrored at the far edge
+        int sh = ph - 1, sw = pw - 1;
+        sh = sh < 0 ? 1 : (sh >= H ? H - 2 : sh);
+        sw = sw < 0 ? 1 : (sw >= W ? W - 2 : sw);
+        const float4* src = reinterpret_cast<const float4*>(buf + (((size_t)b * Hp + sh + 1) * Wp + sw + 1) * C) + c4;
+        float4* dst = reinterpret_cast<float4*>(buf + (((size_t)b * Hp + ph) * Wp + pw) * C) + c4;
+        *dst = *src;
+    }
+}
+
+// ---- host: tensor-map encoding through the driver entry points (no link-time libcuda dependency) ------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+EncodeIm2colFn g_encode_im2col = nullptr;
+
+int load_driver_fns() {
+    if (g_encode_tiled && g_encode_im2col) return 0;
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    SMK_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    SMK_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+    g_encode_tiled = (EncodeTiledFn)fn;
+    SMK_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
+    SMK_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeIm2col not available from the driver");
+    g_encode_im2col = (EncodeIm2colFn)fn;
+    return 0;
+}
+
+int encode_2d(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld_elems * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SMK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r,
+                (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows);
+    return 0;
+}
+
+// NHWC activation tensor [B][Hin][Win][C] (pixel stride ld) read as 3x3 windows; lower/upper corner per CUTLASS
+// conventions: lower = -pad, upper = pad - (3-1).
+int encode_im2col(CUtensorMap* map, const float* base, int B, int Hin, int Win, int C, int ld, int pad) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)Win * ld * 4, (cuuint64_t)Hin * Win * ld * 4};
+    int lower[2] = {-pad, -pad};
+    int upper[2] = {pad - 2, pad - 2};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, lower, upper,
+                                 (cuuint32_t)BK, (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SMK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed (%d): B=%d H=%d W=%d C=%d ld=%d pad=%d", (int)r, B, Hin, Win, C, ld, pad);
+    return 0;
+}
+
+template <int BN, int STAGES>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * BKB) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(cdiv(a.M, BM), cdiv(a.N, BN));
+    gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, a);
+    SMK_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace
+
+int tc_init() { return load_driver_fns(); }
+
+int tc_conv(const TcConv& p, cudaStream_t st) {
+    if (int rc = load_driver_fns()) return rc;
+    const int M = p.B * p.H * p.W;
+    SMK_REQUIRE(p.N % 4 == 0 && p.K % 4 == 0 && p.ld_in % 4 == 0 && p.ld_out % 4 == 0, "tc_conv: N, K, ld must be multiples of 4");
+    SMK_REQUIRE(p.mode == 0 || (p.Cin % BK == 0 && p.K == 9 * p.Cin), "tc_conv: 3x3 mode needs Cin %% 32 == 0 (got %d)", p.Cin);
+    SMK_REQUIRE(p.store != 1 || ((p.N / 4) % 32 == 0), "tc_conv: pixel-shuffle store needs Cout %% 32 == 0");
+    const int BN = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
+    CUtensorMap tmA, tmB;
+    TcArgs a{};
+    a.M = M; a.N = p.N; a.nkb = cdiv(p.K, BK); a.mode = p.mode == 0 ? 0 : 1; a.H = p.H; a.W = p.W;
+    a.cpb = p.mode == 0 ? 1 : p.Cin / BK; a.lc = p.mode == 2 ? 0 : -1;
+    a.scale = p.scale; a.bias = p.bias; a.res = p.res; a.ld_res = p.ld_res; a.res_pad = p.res_pad; a.relu = p.relu;
+    a.out = p.out; a.ld_out = p.ld_out; a.store = p.store;
+    if (p.mode == 0) {
+        if (int rc = encode_2d(&tmA, p.in, (uint64_t)M, (uint64_t)p.K, (uint64_t)p.ld_in, BM)) return rc;
+    } else if (p.mode == 1) {
+        if (int rc = encode_im2col(&tmA, p.in, p.B, p.H, p.W, p.Cin, p.ld_in, 1)) return rc;
+    } else {                                            // input buffer is [B, H+2, W+2, C], already reflection padded
+        if (int rc = encode_im2col(&tmA, p.in, p.B, p.H + 2, p.W + 2, p.Cin, p.ld_in, 0)) return rc;
+    }
+    if (int rc = encode_2d(&tmB, p.wt, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, (uint32_t)BN)) return rc;
+    {
+        const double cin_eff = p.mode == 0 ? p.K : p.Cin;
+        SMK_TAG(p.mode == 0 ? (p.store == 1 ? "upconv_gemm_tc" : "pw_gemm_tc") : "conv3x3_gemm_tc",
+                4.0 * ((double)M * cin_eff + (double)p.K * p.N + (double)M * p.N * (p.res ? 2 : 1) + 2.0 * p.N),
+                2.0 * (double)M * p.N * p.K, st);
+    }
+    if (BN == 32) return launch<32, 6>(tmA, tmB, a, st);
+    if (BN == 64) return launch<64, 6>(tmA, tmB, a, st);
+    return launch<128, 4>(tmA, tmB, a, st);
+}
+
+int reflect_halo(float* buf, int B, int H, int W, int C, cudaStream_t st) {
+    long total = (long)B * (2 * (W + 2) + 2 * H) * (C / 4);
+    SMK_TAG("reflect_halo", 8.0 * (double)total * 4, 0.0, st);
+    reflect_halo_kernel<<<(int)std::min<long>((total + 255) / 256, 148L * 8), 256, 0, st>>>(buf, B, H, W, C);
+    SMK_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace smk
+
+// ---- debug / unit-test entry points (tests/test_gpu_kernels.py) -----------------------------------------
+extern "C" int smk_debug_conv_tc(const float* in, int ld_in, int B, int H, int W, int Cin, const float* wt, const float* scale,
+                                 const float* bias, int N, int K, int mode, int relu, const float* res, int ld_res, int res_pad,
+                                 float* out, int ld_out, int store, void* stream) {
+    smk::TcConv p{};
+    p.in = in; p.ld_in = ld_in; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.wt = wt; p.scale = scale; p.bias = bias; p.N = N; p.K = K;
+    p.mode = mode; p.relu = relu; p.res = res; p.ld_res = ld_res; p.res_pad = res_pad; p.out = out; p.ld_out = ld_out; p.store = store;
+    return smk::tc_conv(p, (cudaStream_t)stream);
+}
+extern "C" int smk_debug_reflect_halo(float* buf, int B, int H, int W, int C, void* stream) {
+    return smk::reflect_halo(buf, B, H, W, C, (cudaStream_t)stream);
+}

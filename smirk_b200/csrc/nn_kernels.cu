@@ -378,3 +378,12 @@ int gap_linear(const float* feat, int B, int HW, int C, const float* w, const fl
 }
 
 }  // namespace smk
+
+extern "C" int smk_debug_conv_f32(const float* in, int ld_in, int B, int H, int W, int Cin, const float* w_kn, const float* scale,
+                                  const float* bias, int N, int K, int mode, int relu, const float* res, int ld_res,
+                                  float* out, int ld_out, int shuffle, void* stream) {
+    smk::ConvProblem p{};
+    p.in = in; p.ld_in = ld_in; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.w = w_kn; p.scale = scale; p.bias = bias; p.N = N; p.K = K;
+    p.mode = mode; p.relu = relu; p.res = res; p.ld_res = ld_res; p.out = out; p.ld_out = ld_out; p.shuffle = shuffle;
+    return smk::conv_gemm(p, (cudaStream_t)stream);
+}

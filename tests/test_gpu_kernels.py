@@ -1,0 +1,176 @@
+"""GPU suite (-m gpu): single convolution kernels through the C ABI's test entry points against
+torch fp32 on the same inputs.  fp32 CUDA-core path: 1e-5 relative.  TF32 tcgen05 path: TF32 operand
+truncation (10-bit mantissa) bounds the error at ~1e-3 of the output scale; the torch reference for
+that path is computed in fp64 so the comparison isolates the kernel's own rounding."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def P(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def make_case(B, H, W, Cin, N, seed, mode):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    k = 1 if mode == 0 else 3
+    w = torch.randn(N, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    scale = torch.rand(N, generator=g) + 0.5
+    bias = torch.randn(N, generator=g) * 0.1
+    return x, w, scale, bias
+
+
+def torch_conv(x, w, scale, bias, mode, relu, res=None, dtype=torch.float64):
+    x, w = x.to(dtype), w.to(dtype)
+    if mode == 2:
+        y = F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), w)
+    else:
+        y = F.conv2d(x, w, padding=1 if mode == 1 else 0)
+    y = y * scale.to(dtype).view(1, -1, 1, 1) + bias.to(dtype).view(1, -1, 1, 1)
+    if res is not None:
+        y = y + res.to(dtype)
+    return (F.relu(y) if relu else y).float()
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def w_kn(w):          # [N,Cin,k,k] -> [K][N], k = (ky*3+kx)*Cin + c
+    N, Cin, k, _ = w.shape
+    return w.permute(2, 3, 1, 0).reshape(k * k * Cin, N).contiguous()
+
+
+def w_nk(w):          # [N,Cin,k,k] -> [N][K]
+    N, Cin, k, _ = w.shape
+    return w.permute(0, 2, 3, 1).reshape(N, k * k * Cin).contiguous()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,N,mode,relu,use_res", [
+    (2, 14, 14, 64, 64, 1, 1, 0), (1, 9, 11, 16, 24, 0, 0, 1), (3, 14, 14, 32, 96, 2, 0, 1),
+    (2, 28, 28, 8, 32, 1, 1, 0), (1, 7, 7, 960, 160, 0, 0, 0), (2, 56, 56, 24, 72, 0, 1, 0),
+])
+def test_conv_f32_kernel(native_lib, B, H, W, Cin, N, mode, relu, use_res):
+    x, w, scale, bias = make_case(B, H, W, Cin, N, 11, mode)
+    res = torch.randn(B, N, H, W) if use_res else None
+    ref = torch_conv(x, w, scale, bias, mode, relu, res)
+    xd, wd = nhwc(x).to(DEV), w_kn(w).to(DEV)
+    out = torch.empty(B, H, W, N, device=DEV)
+    resd = nhwc(res).to(DEV) if use_res else None
+    K = wd.shape[0]
+    rc = native_lib.smk_debug_conv_f32(P(xd), Cin, B, H, W, Cin, P(wd), P(scale.to(DEV)), P(bias.to(DEV)), N, K, mode, relu,
+                                       P(resd), N, P(out), N, 0, stream())
+    assert rc == 0, native_lib.smk_last_error()
+    got = out.permute(0, 3, 1, 2).cpu()
+    assert (got - ref).abs().max() <= 1e-5 * ref.abs().max() + 1e-6
+
+
+def run_tc(native_lib, x, w, scale, bias, mode, relu, res=None, store=0, ld_out=None, out=None):
+    B, Cin, H, W = x.shape
+    N = w.shape[0]
+    xd = nhwc(x).to(DEV)
+    if mode == 2:                                   # kernel wants a padded buffer with reflected halo
+        buf = torch.zeros(B, H + 2, W + 2, Cin, device=DEV)
+        buf[:, 1:-1, 1:-1] = xd
+        assert native_lib.smk_debug_reflect_halo(P(buf), B, H, W, Cin, stream()) == 0
+        ref_pad = nhwc(F.pad(x, (1, 1, 1, 1), mode="reflect")).to(DEV)
+        assert torch.equal(buf, ref_pad)
+        xd = buf
+    wd = w_nk(w).to(DEV)
+    K = wd.shape[1]
+    if out is None:
+        out = torch.full((B, H, W, N), float("nan"), device=DEV)
+    resd = nhwc(res).to(DEV) if res is not None else None
+    rc = native_lib.smk_debug_conv_tc(P(xd), Cin, B, H, W, Cin, P(wd), P(scale.to(DEV)), P(bias.to(DEV)), N, K, mode, relu,
+                                      P(resd), N, 0, P(out), ld_out or N, store, stream())
+    assert rc == 0, native_lib.smk_last_error()
+    torch.cuda.synchronize()
+    return out
+
+
+TC_CASES = [
+    # B, H,  W,  Cin, N,   mode
+    (1, 16, 8, 32, 32, 0),          # one exact 128-row tile, single k-block
+    (2, 14, 14, 64, 64, 0),         # partial last tile (392 rows)
+    (1, 9, 11, 16, 24, 0),          # K < 32 and N < BN: TMA zero-fill on both operands
+    (2, 28, 28, 200, 80, 0),        # K not a multiple of 32, N > 64
+    (1, 7, 7, 960, 160, 0),         # deep K, two N tiles
+    (1, 16, 8, 32, 32, 1),          # 3x3, one tile
+    (2, 14, 14, 64, 128, 1),        # 3x3, tiles cross rows and images, partial tail
+    (3, 14, 14, 32, 96, 2),         # 3x3 over a reflection-padded buffer
+    (2, 28, 28, 128, 256, 1),       # 3x3, two N tiles, 36 k-blocks (ring wraps many times)
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,N,mode", TC_CASES)
+def test_conv_tc_kernel(native_lib, B, H, W, Cin, N, mode):
+    x, w, scale, bias = make_case(B, H, W, Cin, N, 21, mode)
+    res = torch.randn(B, N, H, W)
+    for relu, r in ((1, None), (0, res)):
+        ref = torch_conv(x, w, scale, bias, mode, relu, r)
+        out = run_tc(native_lib, x, w, scale, bias, mode, relu, r)
+        got = out.permute(0, 3, 1, 2).cpu()
+        assert torch.isfinite(got).all(), "unwritten / NaN outputs: %d" % int((~torch.isfinite(got)).sum())
+        err = (got - ref).abs().max().item()
+        assert err <= 3e-3 * ref.abs().max().item(), "max err %.3g vs scale %.3g" % (err, ref.abs().max().item())
+
+
+def test_conv_tc_exact_on_tf32_representable_inputs(native_lib):
+    """With operands exactly representable in TF32 (small integers) the tensor-core result is exact:
+    this pins the im2col addressing, swizzle and descriptor arithmetic independent of rounding."""
+    g = torch.Generator().manual_seed(5)
+    B, H, W, Cin, N = 2, 14, 14, 64, 64
+    x = torch.randint(-3, 4, (B, Cin, H, W), generator=g).float()
+    w = torch.randint(-2, 3, (N, Cin, 3, 3), generator=g).float()
+    one, zero = torch.ones(N), torch.zeros(N)
+    for mode in (1, 2):
+        ref = torch_conv(x, w, one, zero, mode, 0)
+        got = run_tc(native_lib, x, w, one, zero, mode, 0).permute(0, 3, 1, 2).cpu()
+        assert torch.equal(got, ref), "%d mismatches" % int((got != ref).sum())
+    x1 = torch.randint(-3, 4, (1, 40, 9, 11), generator=g).float()
+    w1 = torch.randint(-2, 3, (24, 40, 1, 1), generator=g).float()
+    got = run_tc(native_lib, x1, w1, torch.ones(24), torch.zeros(24), 0, 0).permute(0, 3, 1, 2).cpu()
+    assert torch.equal(got, torch_conv(x1, w1, torch.ones(24), torch.zeros(24), 0, 0))
+
+
+def test_conv_tc_store_modes(native_lib):
+    g = torch.Generator().manual_seed(6)
+    # pixel-shuffle store == ConvTranspose2d(k=2, s=2)
+    B, H, W, Cin, Cout = 2, 14, 14, 64, 32
+    x = torch.randint(-3, 4, (B, Cin, H, W), generator=g).float()
+    wt = torch.randint(-2, 3, (Cin, Cout, 2, 2), generator=g).float()          # ConvTranspose2d weight layout
+    bias = torch.randint(-2, 3, (Cout,), generator=g).float()
+    ref = F.conv_transpose2d(x, wt, bias, stride=2)
+    w_nk_up = wt.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).contiguous()        # n = (dy*2+dx)*Cout + co
+    out = torch.full((B, 2 * H, 2 * W, 2 * Cout), float("nan"), device=DEV)     # lower half of a concat buffer
+    rc = native_lib.smk_debug_conv_tc(P(nhwc(x).to(DEV)), Cin, B, H, W, Cin, P(w_nk_up.to(DEV)), P(torch.ones(4 * Cout, device=DEV)),
+                                      P(bias.repeat(4).to(DEV)), 4 * Cout, Cin, 0, 0, P(None), 0, 0, P(out), 2 * Cout, 1, stream())
+    assert rc == 0, native_lib.smk_last_error()
+    torch.cuda.synchronize()
+    assert torch.equal(out[..., :Cout].permute(0, 3, 1, 2).cpu(), ref)
+    assert torch.isnan(out[..., Cout:]).all()                                   # the other slice is untouched
+    # padded-interior store + residual read from a padded buffer
+    x, w, scale, bias = make_case(2, 14, 14, 32, 64, 8, 1)
+    res = torch.randn(2, 64, 14, 14, generator=g)
+    res_pad = torch.zeros(2, 16, 16, 64, device=DEV)
+    res_pad[:, 1:-1, 1:-1] = nhwc(res).to(DEV)
+    outp = torch.full((2, 16, 16, 64), float("nan"), device=DEV)
+    wd = w_nk(w).to(DEV)
+    rc = native_lib.smk_debug_conv_tc(P(nhwc(x).to(DEV)), 32, 2, 14, 14, 32, P(wd), P(scale.to(DEV)), P(bias.to(DEV)), 64, 288, 1, 0,
+                                      P(res_pad), 64, 1, P(outp), 64, 2, stream())
+    assert rc == 0, native_lib.smk_last_error()
+    torch.cuda.synchronize()
+    ref = torch_conv(x, w, scale, bias, 1, 0, res)
+    got = outp[:, 1:-1, 1:-1].permute(0, 3, 1, 2).cpu()
+    assert (got - ref).abs().max() <= 3e-3 * ref.abs().max()
+    assert torch.isnan(outp[:, 0]).all() and torch.isnan(outp[:, :, 0]).all()
