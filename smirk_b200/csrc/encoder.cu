@@ -6,6 +6,7 @@
 // heads/clamps at :34-45, :66-73, :95-110.  BatchNorm (eval mode) is folded into a per-channel
 // scale/bias applied in each convolution's epilogue; activations live in NHWC fp32.
 #include "nn_kernels.cuh"
+#include "gemm_tc.cuh"
 #include <math.h>
 
 namespace {
@@ -14,7 +15,7 @@ using smk::ConvProblem;
 
 constexpr float kBnEps = 1e-3f;
 
-struct ConvW { float* w = nullptr; float* scale = nullptr; float* bias = nullptr; int cin = 0, cout = 0; };
+struct ConvW { float* w = nullptr; float* wt = nullptr; float* scale = nullptr; float* bias = nullptr; int cin = 0, cout = 0; };   // w: [K][N] fp32 path, wt: [N][K] tcgen05 path
 enum Kind { DS = 0, IR = 1, CN = 2 };
 struct BlockDef { Kind kind; int stride; float exp; int cout; };
 struct Block { Kind kind; int stride, cin, mid, cout; bool skip; ConvW pw, dw, pwl; };
@@ -57,12 +58,14 @@ struct TensorCursor {
 };
 
 // kind: 0 = 1x1 [Cout,Cin,1,1] -> W[Cin][Cout]; 1 = depthwise [C,1,3,3] -> W[9][C]; 2 = stem [16,3,3,3] -> W[27][16]
-bool fold_conv(TensorCursor& cur, int kind, int cin, int cout, smk::DeviceArena& arena, ConvW* out, cudaError_t* err) {
+bool fold_conv(TensorCursor& cur, int kind, int cin, int cout, bool tc, smk::DeviceArena& arena, ConvW* out, cudaError_t* err) {
     const float* w = cur.next(); const float* g = cur.next(); const float* b = cur.next();
     const float* mu = cur.next(); const float* var = cur.next();
     if (!w || !g || !b || !mu || !var) return false;
     std::vector<float> W, S(cout), Bi(cout);
-    if (kind == 0) {
+    if (kind == 0 && tc) {
+        W.assign(w, w + (size_t)cin * cout);                 // torch layout [Cout][Cin] is already [N][K]
+    } else if (kind == 0) {
         W.resize((size_t)cin * cout);
         for (int o = 0; o < cout; ++o) for (int c = 0; c < cin; ++c) W[(size_t)c * cout + o] = w[(size_t)o * cin + c];
     } else if (kind == 1) {
@@ -77,7 +80,7 @@ bool fold_conv(TensorCursor& cur, int kind, int cin, int cout, smk::DeviceArena&
         S[o] = s; Bi[o] = b[o] - mu[o] * s;
     }
     out->cin = cin; out->cout = cout;
-    cudaError_t e = arena.upload(W, &out->w);
+    cudaError_t e = arena.upload(W, (kind == 0 && tc) ? &out->wt : &out->w);
     if (e == cudaSuccess) e = arena.upload(S, &out->scale);
     if (e == cudaSuccess) e = arena.upload(Bi, &out->bias);
     *err = e;
@@ -95,7 +98,9 @@ struct SmkEncoder {
 
 extern "C" int smk_encoder_create(const SmkEncoderDesc* desc, SmkEncoder** out) {
     SMK_REQUIRE(desc && out, "smk_encoder_create: null argument");
-    SMK_REQUIRE(desc->precision == 0, "smk_encoder_create: precision %d not available for the encoder yet", desc->precision);
+    SMK_REQUIRE(desc->precision == 0 || desc->precision == 1, "smk_encoder_create: precision must be 0 (fp32) or 1 (tf32 tcgen05 1x1 convs)");
+    if (desc->precision == 1) { if (int rc = smk::tc_init()) return rc; }
+    const bool tc = desc->precision == 1;
     SmkEncoder* h = new SmkEncoder();
     h->n_shape = desc->n_shape; h->n_exp = desc->n_exp; h->precision = desc->precision;
     const int n_outs[3] = {6, desc->n_shape, desc->n_exp + 5};
@@ -105,7 +110,7 @@ extern "C" int smk_encoder_create(const SmkEncoderDesc* desc, SmkEncoder** out) 
         const int nb = i == 0 ? (int)(sizeof(kSmall) / sizeof(BlockDef)) : (int)(sizeof(kLarge) / sizeof(BlockDef));
         Backbone& bb = h->bb[i];
         TensorCursor cur{desc->tensors[i], desc->n_tensors[i]};
-        bool ok = fold_conv(cur, 2, 3, 16, h->arena, &bb.stem, &e);
+        bool ok = fold_conv(cur, 2, 3, 16, false, h->arena, &bb.stem, &e);
         int cin = 16, res = 112;
         size_t max_act = (size_t)112 * 112 * 16;
         for (int k = 0; ok && k < nb; ++k) {
@@ -114,14 +119,14 @@ extern "C" int smk_encoder_create(const SmkEncoderDesc* desc, SmkEncoder** out) 
             b.skip = b.kind != CN && b.stride == 1 && b.cin == b.cout;
             if (b.kind == DS) {
                 b.mid = cin;
-                ok = fold_conv(cur, 1, cin, cin, h->arena, &b.dw, &e) && fold_conv(cur, 0, cin, b.cout, h->arena, &b.pw, &e);
+                ok = fold_conv(cur, 1, cin, cin, false, h->arena, &b.dw, &e) && fold_conv(cur, 0, cin, b.cout, tc, h->arena, &b.pw, &e);
             } else if (b.kind == IR) {
                 b.mid = make_divisible((double)cin * defs[k].exp);
-                ok = fold_conv(cur, 0, cin, b.mid, h->arena, &b.pw, &e) && fold_conv(cur, 1, b.mid, b.mid, h->arena, &b.dw, &e) &&
-                     fold_conv(cur, 0, b.mid, b.cout, h->arena, &b.pwl, &e);
+                ok = fold_conv(cur, 0, cin, b.mid, tc, h->arena, &b.pw, &e) && fold_conv(cur, 1, b.mid, b.mid, false, h->arena, &b.dw, &e) &&
+                     fold_conv(cur, 0, b.mid, b.cout, tc, h->arena, &b.pwl, &e);
             } else {
                 b.mid = cin;
-                ok = fold_conv(cur, 0, cin, b.cout, h->arena, &b.pw, &e);
+                ok = fold_conv(cur, 0, cin, b.cout, tc, h->arena, &b.pw, &e);
             }
             max_act = std::max(max_act, (size_t)res * res * b.mid);           // expanded tensor at input resolution
             res = (res + b.stride - 1) / b.stride;
@@ -158,6 +163,13 @@ extern "C" size_t smk_encoder_workspace_bytes(const SmkEncoder* h, int B) {
 }
 
 static int pointwise(const ConvW& c, const float* in, int B, int H, int W, bool relu, const float* res, float* out, cudaStream_t st) {
+    if (c.wt) {
+        smk::TcConv q{};
+        q.in = in; q.ld_in = c.cin; q.B = B; q.H = H; q.W = W; q.Cin = c.cin; q.wt = c.wt; q.scale = c.scale; q.bias = c.bias;
+        q.N = c.cout; q.K = c.cin; q.mode = 0; q.relu = relu ? 1 : 0; q.res = res; q.ld_res = c.cout; q.res_pad = 0;
+        q.out = out; q.ld_out = c.cout; q.store = 0;
+        return smk::tc_conv(q, st);
+    }
     ConvProblem p{};
     p.in = in; p.ld_in = c.cin; p.B = B; p.H = H; p.W = W; p.Cin = c.cin;
     p.w = c.w; p.scale = c.scale; p.bias = c.bias; p.N = c.cout; p.K = c.cin; p.mode = 0; p.relu = relu ? 1 : 0;

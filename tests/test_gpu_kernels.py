@@ -68,7 +68,8 @@ def test_conv_f32_kernel(native_lib, B, H, W, Cin, N, mode, relu, use_res):
     out = torch.empty(B, H, W, N, device=DEV)
     resd = nhwc(res).to(DEV) if use_res else None
     K = wd.shape[0]
-    rc = native_lib.smk_debug_conv_f32(P(xd), Cin, B, H, W, Cin, P(wd), P(scale.to(DEV)), P(bias.to(DEV)), N, K, mode, relu,
+    sd, bd = scale.to(DEV), bias.to(DEV)            # keep device tensors alive across the call
+    rc = native_lib.smk_debug_conv_f32(P(xd), Cin, B, H, W, Cin, P(wd), P(sd), P(bd), N, K, mode, relu,
                                        P(resd), N, P(out), N, 0, stream())
     assert rc == 0, native_lib.smk_last_error()
     got = out.permute(0, 3, 1, 2).cpu()
@@ -91,7 +92,8 @@ def run_tc(native_lib, x, w, scale, bias, mode, relu, res=None, store=0, ld_out=
     if out is None:
         out = torch.full((B, H, W, N), float("nan"), device=DEV)
     resd = nhwc(res).to(DEV) if res is not None else None
-    rc = native_lib.smk_debug_conv_tc(P(xd), Cin, B, H, W, Cin, P(wd), P(scale.to(DEV)), P(bias.to(DEV)), N, K, mode, relu,
+    sd, bd = scale.to(DEV), bias.to(DEV)            # keep device tensors alive across the call
+    rc = native_lib.smk_debug_conv_tc(P(xd), Cin, B, H, W, Cin, P(wd), P(sd), P(bd), N, K, mode, relu,
                                       P(resd), N, 0, P(out), ld_out or N, store, stream())
     assert rc == 0, native_lib.smk_last_error()
     torch.cuda.synchronize()
@@ -153,8 +155,9 @@ def test_conv_tc_store_modes(native_lib):
     ref = F.conv_transpose2d(x, wt, bias, stride=2)
     w_nk_up = wt.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).contiguous()        # n = (dy*2+dx)*Cout + co
     out = torch.full((B, 2 * H, 2 * W, 2 * Cout), float("nan"), device=DEV)     # lower half of a concat buffer
-    rc = native_lib.smk_debug_conv_tc(P(nhwc(x).to(DEV)), Cin, B, H, W, Cin, P(w_nk_up.to(DEV)), P(torch.ones(4 * Cout, device=DEV)),
-                                      P(bias.repeat(4).to(DEV)), 4 * Cout, Cin, 0, 0, P(None), 0, 0, P(out), 2 * Cout, 1, stream())
+    xd, wd, sd, bd = nhwc(x).to(DEV), w_nk_up.to(DEV), torch.ones(4 * Cout, device=DEV), bias.repeat(4).to(DEV)
+    rc = native_lib.smk_debug_conv_tc(P(xd), Cin, B, H, W, Cin, P(wd), P(sd), P(bd), 4 * Cout, Cin, 0, 0, P(None), 0, 0,
+                                      P(out), 2 * Cout, 1, stream())
     assert rc == 0, native_lib.smk_last_error()
     torch.cuda.synchronize()
     assert torch.equal(out[..., :Cout].permute(0, 3, 1, 2).cpu(), ref)
@@ -165,8 +168,8 @@ def test_conv_tc_store_modes(native_lib):
     res_pad = torch.zeros(2, 16, 16, 64, device=DEV)
     res_pad[:, 1:-1, 1:-1] = nhwc(res).to(DEV)
     outp = torch.full((2, 16, 16, 64), float("nan"), device=DEV)
-    wd = w_nk(w).to(DEV)
-    rc = native_lib.smk_debug_conv_tc(P(nhwc(x).to(DEV)), 32, 2, 14, 14, 32, P(wd), P(scale.to(DEV)), P(bias.to(DEV)), 64, 288, 1, 0,
+    wd, xd, sd, bd = w_nk(w).to(DEV), nhwc(x).to(DEV), scale.to(DEV), bias.to(DEV)
+    rc = native_lib.smk_debug_conv_tc(P(xd), 32, 2, 14, 14, 32, P(wd), P(sd), P(bd), 64, 288, 1, 0,
                                       P(res_pad), 64, 1, P(outp), 64, 2, stream())
     assert rc == 0, native_lib.smk_last_error()
     torch.cuda.synchronize()
