@@ -180,6 +180,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16, help="faces per CPU-baseline pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel breakdown JSON here")
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
+                    help="tf32: 1x1/3x3/transposed convs on tcgen05 tensor cores (the reference's own cuDNN default); "
+                         "fp32: every conv on the exact fp32 CUDA-core path")
     args = ap.parse_args()
     if args.profile_out:
         args.profile_out = os.path.abspath(args.profile_out)
@@ -217,11 +220,13 @@ def main():
     enc = smirk_b200.SmirkEncoder()
     enc.load_state_dict(synth_inputs.random_state_dict(enc.state_dict(), seed=7))
     enc = enc.eval().to(dev)
+    enc.precision = 1 if args.precision == "tf32" else 0
     gen = None
     if args.generator:
         gen = smirk_b200.SmirkGenerator(6, 3, 32, 5)
         gen.load_state_dict(synth_inputs.random_state_dict(gen.state_dict(), seed=7))
         gen = gen.eval().to(dev)
+        gen.precision = enc.precision
     pipe = SmirkPipeline(enc, smirk_b200.FLAME().to(dev), smirk_b200.Renderer().to(dev), gen, device=dev)
 
     # rotating input set larger than L2 (126 MB): R batches of B x 602 KB
@@ -330,8 +335,8 @@ def main():
         line = {
             "metric": METRIC, "value": faces / (ms_total / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "global_batch": B * world, "faces_per_gpu_per_step": B,
+            "dtype": "tf32 convs (fp32 accumulate), f32 elsewhere" if args.precision == "tf32" else "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "precision": args.precision, "global_batch": B * world, "faces_per_gpu_per_step": B,
                        "image": "224x224 RGB fp32", "parallelism": "frame-shard dp%d" % world,
                        "l2_policy": "inputs rotate over %d batches (%.0f MB > 126 MB L2)" % (R, R * per / 1e6),
                        "execution": "CUDA graph replay, %d kernels per step" % rec["launches"]},

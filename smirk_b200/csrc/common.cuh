@@ -66,4 +66,23 @@ static inline size_t ws_round(size_t bytes) { return (bytes + 255) & ~size_t(255
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// TF32 rounding (round-to-nearest, ties away: PTX cvt.rna).  The tensor cores read fp32 words from shared
+// memory and simply ignore the 13 low mantissa bits (truncation, a systematic bias); operands that feed
+// a tcgen05 layer are therefore rounded once, where they are produced: weights on the host at pack
+// time, activations in the epilogue of the kernel that writes them — what cuDNN/CUTLASS TF32 kernels
+// do with cvt.rna in registers before mma.
+#ifdef __CUDACC__
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+#endif
+static inline float round_tf32_host(float x) {
+    uint32_t u; memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return x;          // inf / nan
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    float r; memcpy(&r, &u, 4); return r;
+}
+
 }  // namespace smk

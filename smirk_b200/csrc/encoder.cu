@@ -64,7 +64,8 @@ bool fold_conv(TensorCursor& cur, int kind, int cin, int cout, bool tc, smk::Dev
     if (!w || !g || !b || !mu || !var) return false;
     std::vector<float> W, S(cout), Bi(cout);
     if (kind == 0 && tc) {
-        W.assign(w, w + (size_t)cin * cout);                 // torch layout [Cout][Cin] is already [N][K]
+        W.resize((size_t)cin * cout);                        // torch layout [Cout][Cin] is already [N][K]
+        for (size_t i = 0; i < W.size(); ++i) W[i] = smk::round_tf32_host(w[i]);
     } else if (kind == 0) {
         W.resize((size_t)cin * cout);
         for (int o = 0; o < cout; ++o) for (int c = 0; c < cin; ++c) W[(size_t)c * cout + o] = w[(size_t)o * cin + c];
@@ -167,7 +168,7 @@ static int pointwise(const ConvW& c, const float* in, int B, int H, int W, bool 
         smk::TcConv q{};
         q.in = in; q.ld_in = c.cin; q.B = B; q.H = H; q.W = W; q.Cin = c.cin; q.wt = c.wt; q.scale = c.scale; q.bias = c.bias;
         q.N = c.cout; q.K = c.cin; q.mode = 0; q.relu = relu ? 1 : 0; q.res = res; q.ld_res = c.cout; q.res_pad = 0;
-        q.out = out; q.ld_out = c.cout; q.store = 0;
+        q.out = out; q.ld_out = c.cout; q.store = 0; q.round_out = 1;
         return smk::tc_conv(q, st);
     }
     ConvProblem p{};
@@ -197,11 +198,11 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
         for (const Block& b : bb.blocks) {
             int ro = (res + b.stride - 1) / b.stride;
             if (b.kind == DS) {
-                rc = smk::dwconv3x3(x, B, res, res, b.cin, b.stride, b.dw.w, b.dw.scale, b.dw.bias, d, st);
+                rc = smk::dwconv3x3(x, B, res, res, b.cin, b.stride, b.dw.w, b.dw.scale, b.dw.bias, d, st, h->precision == 1);
                 if (!rc) rc = pointwise(b.pw, d, B, ro, ro, false, b.skip ? x : nullptr, y, st);
             } else if (b.kind == IR) {
                 rc = pointwise(b.pw, x, B, res, res, true, nullptr, e, st);
-                if (!rc) rc = smk::dwconv3x3(e, B, res, res, b.mid, b.stride, b.dw.w, b.dw.scale, b.dw.bias, d, st);
+                if (!rc) rc = smk::dwconv3x3(e, B, res, res, b.mid, b.stride, b.dw.w, b.dw.scale, b.dw.bias, d, st, h->precision == 1);
                 if (!rc) rc = pointwise(b.pwl, d, B, ro, ro, false, b.skip ? x : nullptr, y, st);
             } else {
                 rc = pointwise(b.pw, x, B, res, res, true, nullptr, y, st);
@@ -210,7 +211,7 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
             std::swap(x, y);
             res = ro;
         }
-        rc = smk::gap_linear(x, B, res * res, bb.feat, bb.head_w, bb.head_b, bb.n_out, bb.codes, outs[i], st);
+        rc = smk::gap_linear(x, B, res * res, bb.feat, bb.head_w, bb.head_b, bb.n_out, bb.codes, y, outs[i], st);
         if (rc) return rc;
     }
     return 0;

@@ -122,10 +122,11 @@ struct TcArgs {
     int relu;
     float* out; int ld_out;
     int store;                     // 0 plain, 1 pixel-shuffle (N = 4*Cout), 2 interior of a (H+2)x(W+2) padded buffer
+    int round_out;                 // 1: round the stored activations to TF32 (round-to-nearest) for the next tensor-core layer
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, int STAGES, int MINB>
+__global__ void __launch_bounds__(NUM_THREADS, MINB)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     constexpr int B_STAGE_BYTES = BN * BKB;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -203,47 +204,71 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
         mbar_wait(tmem_full, 0);
         tcgen05_fence_after();
+        // Two phases per 32-column chunk, both private to the warp (it owns TMEM lanes / tile rows
+        // [32*quarter, +32)), so only __syncwarp separates them:
+        //   1. lane = row: tcgen05.ld 32 accumulator columns and park them in a 32 x 128-byte staging
+        //      slab in shared memory (16-byte chunks XOR-swizzled by row: conflict-free both ways);
+        //   2. 8 lanes per row, 4 rows per instruction: read the slab back transposed, apply
+        //      scale/bias (+residual) (+ReLU) (+TF32 rounding) and store — every global access of the
+        //      warp now covers whole 128-byte lines of 4 output rows instead of 16 bytes of 32 rows.
+        // The pipeline stages are idle by now (tmem_full fires after the last MMA has read them), so
+        // stage 0's A slab (16 KiB) doubles as the staging buffer: 4 KiB per epilogue warp.
         const int quarter = warp & 3;
-        const int row = quarter * 32 + lane;
-        const int m = m0 + row;
-        const bool row_ok = m < a.M;
-        size_t out_pix = (size_t)(row_ok ? m : 0), res_pix = out_pix;
-        int b = 0, h = 0, w = 0;
-        if (a.store != 0 || a.res_pad) {
-            int hw = a.H * a.W; int mm = row_ok ? m : 0;
-            b = mm / hw; int r = mm - b * hw; h = r / a.W; w = r - h * a.W;
-            size_t padded = ((size_t)b * (a.H + 2) + h + 1) * (a.W + 2) + w + 1;
-            if (a.store == 2) out_pix = padded;
-            if (a.res_pad) res_pix = padded;
+        uint8_t* slab = smem + quarter * 4096;
+        const int sub = lane >> 3, jj = lane & 7;              // phase-2 role: row-in-group, 16-byte chunk
+        int opix[8], rpix[8];                                  // destination / residual pixel of my 8 phase-2 rows (-1: past M)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + quarter * 32 + 4 * i + sub;
+            int o = -1, r = -1;
+            if (m < a.M) {
+                o = r = m;
+                if (a.store != 0 || a.res_pad) {
+                    const int hw = a.H * a.W, b = m / hw, rem = m - b * hw, h = rem / a.W, w = rem - h * a.W;
+                    const int padded = (b * (a.H + 2) + h + 1) * (a.W + 2) + w + 1;
+                    if (a.store == 2) o = padded;
+                    else if (a.store == 1) o = (b * (2 * a.H) + 2 * h) * (2 * a.W) + 2 * w;
+                    if (a.res_pad) r = padded;
+                }
+            }
+            opix[i] = o; rpix[i] = r;
         }
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);     // warp-collective
             const int n = n0 + c0;
-            if (!row_ok || n >= a.N) continue;
-            const int nv = min(32, a.N - n);
-            float* dst;
-            if (a.store == 1) {                      // ConvTranspose2d k2 s2: n = (dy*2+dx)*Cout + co
-                int cout = a.N >> 2, q = n / cout, co = n - q * cout;
-                size_t dp = ((size_t)b * (2 * a.H) + 2 * h + (q >> 1)) * (2 * a.W) + 2 * w + (q & 1);
-                dst = a.out + dp * a.ld_out + co;
-            } else {
-                dst = a.out + out_pix * a.ld_out + n;
-            }
-            const float* rs = a.res ? a.res + res_pix * a.ld_res + n : nullptr;
+            if (n >= a.N) break;                               // warp-uniform
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                if (j >= nv) break;
-                float4 sc = *reinterpret_cast<const float4*>(a.scale + n + j);
-                float4 bi = *reinterpret_cast<const float4*>(a.bias + n + j);
-                float4 o;
-                o.x = fmaf(v[j], sc.x, bi.x); o.y = fmaf(v[j + 1], sc.y, bi.y);
-                o.z = fmaf(v[j + 2], sc.z, bi.z); o.w = fmaf(v[j + 3], sc.w, bi.w);
-                if (rs) { float4 r4 = *reinterpret_cast<const float4*>(rs + j); o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
-                if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                *reinterpret_cast<float4*>(dst + j) = o;
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+            const int nc = n + jj * 4;                         // my 4 columns
+            if (nc < a.N) {
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + nc));
+                const float4 bi = __ldg(reinterpret_cast<const float4*>(a.bias + nc));
+                int col = nc, pix_off = 0;
+                if (a.store == 1) {                            // ConvTranspose2d k2 s2: n = (dy*2+dx)*Cout + co
+                    const int cout = a.N >> 2, q = nc / cout;
+                    col = nc - q * cout; pix_off = (q >> 1) * (2 * a.W) + (q & 1);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (opix[i] < 0) continue;
+                    const int r = 4 * i + sub;
+                    const float4 x = *reinterpret_cast<const float4*>(slab + r * 128 + ((jj ^ (r & 7)) << 4));
+                    float4 o;
+                    o.x = fmaf(x.x, sc.x, bi.x); o.y = fmaf(x.y, sc.y, bi.y); o.z = fmaf(x.z, sc.z, bi.z); o.w = fmaf(x.w, sc.w, bi.w);
+                    if (a.res) {
+                        const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.res + (size_t)rpix[i] * a.ld_res + nc));
+                        o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                    }
+                    if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (a.round_out) { o.x = smk::round_tf32(o.x); o.y = smk::round_tf32(o.y); o.z = smk::round_tf32(o.z); o.w = smk::round_tf32(o.w); }
+                    *reinterpret_cast<float4*>(a.out + (size_t)(opix[i] + pix_off) * a.ld_out + col) = o;
+                }
             }
+            __syncwarp();
         }
         tcgen05_fence_before();
     }
@@ -327,16 +352,16 @@ int encode_im2col(CUtensorMap* map, const float* base, int B, int Hin, int Win, 
     return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MINB>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * BKB) + 1024 + 256;
     static bool configured = false;
     if (!configured) {
-        SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     dim3 grid(cdiv(a.M, BM), cdiv(a.N, BN));
-    gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, a);
+    gemm_tc_kernel<BN, STAGES, MINB><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, a);
     SMK_CHECK_LAUNCH();
     return 0;
 }
@@ -357,7 +382,7 @@ int tc_conv(const TcConv& p, cudaStream_t st) {
     a.M = M; a.N = p.N; a.nkb = cdiv(p.K, BK); a.mode = p.mode == 0 ? 0 : 1; a.H = p.H; a.W = p.W;
     a.cpb = p.mode == 0 ? 1 : p.Cin / BK; a.lc = p.mode == 2 ? 0 : -1;
     a.scale = p.scale; a.bias = p.bias; a.res = p.res; a.ld_res = p.ld_res; a.res_pad = p.res_pad; a.relu = p.relu;
-    a.out = p.out; a.ld_out = p.ld_out; a.store = p.store;
+    a.out = p.out; a.ld_out = p.ld_out; a.store = p.store; a.round_out = p.round_out;
     if (p.mode == 0) {
         if (int rc = encode_2d(&tmA, p.in, (uint64_t)M, (uint64_t)p.K, (uint64_t)p.ld_in, BM)) return rc;
     } else if (p.mode == 1) {
@@ -372,9 +397,12 @@ int tc_conv(const TcConv& p, cudaStream_t st) {
                 4.0 * ((double)M * cin_eff + (double)p.K * p.N + (double)M * p.N * (p.res ? 2 : 1) + 2.0 * p.N),
                 2.0 * (double)M * p.N * p.K, st);
     }
-    if (BN == 32) return launch<32, 6>(tmA, tmB, a, st);
-    if (BN == 64) return launch<64, 6>(tmA, tmB, a, st);
-    return launch<128, 4>(tmA, tmB, a, st);
+    // Shallow-K layers (the encoder's 1x1 convs) are HBM-bound: a 2-stage ring keeps the footprint small so
+    // 3-5 CTAs share an SM and hide each other's prologue/epilogue; deep-K layers get a deeper ring.
+    const bool shallow = a.nkb <= 2;
+    if (BN == 32) return shallow ? launch<32, 2, 5>(tmA, tmB, a, st) : launch<32, 4, 2>(tmA, tmB, a, st);
+    if (BN == 64) return shallow ? launch<64, 2, 4>(tmA, tmB, a, st) : launch<64, 4, 2>(tmA, tmB, a, st);
+    return shallow ? launch<128, 2, 3>(tmA, tmB, a, st) : launch<128, 3, 2>(tmA, tmB, a, st);
 }
 
 int reflect_halo(float* buf, int B, int H, int W, int C, cudaStream_t st) {

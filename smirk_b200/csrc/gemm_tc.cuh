@@ -15,6 +15,7 @@ struct TcConv {
     const float* res; int ld_res; int res_pad;   // residual; res_pad: read it from the interior of a padded buffer
     float* out; int ld_out;
     int store;                           // 0 plain, 1 pixel-shuffle (N = 4*Cout), 2 interior of a (H+2)x(W+2) padded buffer
+    int round_out;                       // 1: round stored activations to TF32 (RN) — they feed another tensor-core layer
 };
 
 int tc_init();                                              // resolves the driver's tensor-map encoders

@@ -41,7 +41,7 @@ bool fold_conv3(TensorCursor& cur, int cin, int cin_p, int cout, bool tc, smk::D
         for (int c = 0; c < cin; ++c)
             for (int k = 0; k < 9; ++k) {
                 float v = w[((size_t)o * cin + c) * 9 + k];
-                if (tc) W[(size_t)o * K + (size_t)k * cin_p + c] = v;          // [N][K]
+                if (tc) W[(size_t)o * K + (size_t)k * cin_p + c] = smk::round_tf32_host(v);   // [N][K], TF32-rounded
                 else W[((size_t)k * cin_p + c) * cout + o] = v;                // [K][N]
             }
     for (int o = 0; o < cout; ++o) {
@@ -64,7 +64,7 @@ bool fold_upconv(TensorCursor& cur, int cin, int cout, bool tc, smk::DeviceArena
         for (int o = 0; o < cout; ++o)
             for (int q = 0; q < 4; ++q) {
                 float v = w[((size_t)c * cout + o) * 4 + q];
-                if (tc) W[((size_t)q * cout + o) * cin + c] = v;               // [N = 4*cout][K = cin]
+                if (tc) W[((size_t)q * cout + o) * cin + c] = smk::round_tf32_host(v);   // [N = 4*cout][K = cin]
                 else W[(size_t)c * 4 * cout + q * cout + o] = v;               // [K][N]
             }
     for (int q = 0; q < 4; ++q) for (int o = 0; o < cout; ++o) Bi[q * cout + o] = b[o];
@@ -172,13 +172,13 @@ int conv3(const SmkGenerator* h, const Conv3& c, const float* in, int ld_in, int
         TcConv p{};
         p.in = in; p.ld_in = ld_in; p.B = B; p.H = S; p.W = S; p.Cin = c.cin_p; p.wt = c.wt; p.scale = c.scale; p.bias = c.bias;
         p.N = c.cout; p.K = 9 * c.cin_p; p.mode = refl ? 2 : 1; p.relu = relu ? 1 : 0;
-        p.res = res; p.ld_res = c.cout; p.res_pad = res_pad; p.out = out; p.ld_out = ld_out; p.store = store;
+        p.res = res; p.ld_res = c.cout; p.res_pad = res_pad; p.out = out; p.ld_out = ld_out; p.store = store; p.round_out = 1;
         return smk::tc_conv(p, st);
     }
     ConvProblem p{};
     p.in = in; p.ld_in = ld_in; p.B = B; p.H = S; p.W = S; p.Cin = c.cin_p;
     p.w = c.w; p.scale = c.scale; p.bias = c.bias; p.N = c.cout; p.K = 9 * c.cin_p; p.mode = refl ? 2 : 1; p.relu = relu ? 1 : 0;
-    p.res = res; p.ld_res = c.cout; p.out = out; p.ld_out = ld_out; p.shuffle = 0;
+    p.res = res; p.ld_res = c.cout; p.out = out; p.ld_out = ld_out; p.shuffle = 0; p.round_out = h->precision == 1 ? 1 : 0;
     return smk::conv_gemm(p, st);
 }
 }  // namespace
@@ -253,7 +253,7 @@ extern "C" int smk_generator_forward(const SmkGenerator* h, const float* x, int 
         if (u.wt) {
             TcConv q{};
             q.in = din; q.ld_in = u.cin; q.B = B; q.H = dS; q.W = dS; q.Cin = u.cin; q.wt = u.wt; q.scale = u.scale; q.bias = u.bias;
-            q.N = 4 * u.cout; q.K = u.cin; q.mode = 0; q.relu = 0; q.res = nullptr; q.out = cat[lvl]; q.ld_out = 2 * u.cout; q.store = 1;
+            q.N = 4 * u.cout; q.K = u.cin; q.mode = 0; q.relu = 0; q.res = nullptr; q.out = cat[lvl]; q.ld_out = 2 * u.cout; q.store = 1; q.round_out = 1;
             if ((rc = smk::tc_conv(q, st))) return rc;
         } else {
             ConvProblem q{};

@@ -124,6 +124,7 @@ conv_gemm_kernel(ConvProblem p, int M) {
             float v = fmaf(acc[i][j], p.scale[n], p.bias[n]);
             if (p.res) v += p.res[(size_t)m * p.ld_res + n];
             if (p.relu) v = fmaxf(v, 0.f);
+            if (p.round_out) v = round_tf32(v);
             if (p.shuffle) {
                 int cout = p.N >> 2, q = n / cout, co = n - q * cout;
                 int b = m / HW, r = m - b * HW, h = r / p.W, w = r - h * p.W;
@@ -166,6 +167,99 @@ dwconv3x3_kernel(const float* __restrict__ in, int B, int H, int W, int C, int s
         o.x = fmaxf(fmaf(acc.x, s.x, bb.x), 0.f); o.y = fmaxf(fmaf(acc.y, s.y, bb.y), 0.f);
         o.z = fmaxf(fmaf(acc.z, s.z, bb.z), 0.f); o.w = fmaxf(fmaf(acc.w, s.w, bb.w), 0.f);
         *reinterpret_cast<float4*>(out + (size_t)pix * C + c4 * 4) = o;
+    }
+}
+
+// Depthwise 3x3, 4 output pixels along W x 4 channels per thread: the 3 x (3 + 3*STRIDE) input window is
+// loaded once (float4 per pixel) and reused by the 4 outputs; weights stay in registers.
+template <int STRIDE>
+__global__ void __launch_bounds__(256)
+dwconv3x3_px4_kernel(const float* __restrict__ in, int B, int H, int W, int C, int pad, int Ho, int Wo,
+                     const float* __restrict__ w9c, const float* __restrict__ scale, const float* __restrict__ bias,
+                     float* __restrict__ out, int round_out) {
+    constexpr int PX = 4, NC = 3 + (PX - 1) * STRIDE;
+    const int C4 = C >> 2, WG = (Wo + PX - 1) / PX;
+    const long total = (long)B * Ho * WG * C4;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int c4 = (int)(i % C4); long t = i / C4;
+        int wg = (int)(t % WG); t /= WG; int oh = (int)(t % Ho); int b = (int)(t / Ho);
+        const int ow0 = wg * PX, iw0 = ow0 * STRIDE - pad;
+        float4 k[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) k[q] = __ldg(reinterpret_cast<const float4*>(w9c + (size_t)q * C) + c4);
+        float4 acc[PX];
+#pragma unroll
+        for (int p = 0; p < PX; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            int ih = oh * STRIDE + ky - pad;
+            if (ih < 0 || ih >= H) continue;
+            const float4* row = reinterpret_cast<const float4*>(in + ((size_t)b * H + ih) * W * C) + c4;
+            float4 x[NC];
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                int iw = iw0 + j;
+                x[j] = (iw >= 0 && iw < W) ? __ldg(row + (size_t)iw * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int p = 0; p < PX; ++p)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4 xv = x[p * STRIDE + kx], kv = k[ky * 3 + kx];
+                    acc[p].x = fmaf(xv.x, kv.x, acc[p].x); acc[p].y = fmaf(xv.y, kv.y, acc[p].y);
+                    acc[p].z = fmaf(xv.z, kv.z, acc[p].z); acc[p].w = fmaf(xv.w, kv.w, acc[p].w);
+                }
+        }
+        const float4 s = __ldg(reinterpret_cast<const float4*>(scale) + c4), bb = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+        float4* orow = reinterpret_cast<float4*>(out + (((size_t)b * Ho + oh) * Wo) * C) + c4;
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            if (ow0 + p >= Wo) break;
+            float4 o;
+            o.x = fmaxf(fmaf(acc[p].x, s.x, bb.x), 0.f); o.y = fmaxf(fmaf(acc[p].y, s.y, bb.y), 0.f);
+            o.z = fmaxf(fmaf(acc[p].z, s.z, bb.z), 0.f); o.w = fmaxf(fmaf(acc[p].w, s.w, bb.w), 0.f);
+            if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+            orow[(size_t)(ow0 + p) * C4] = o;
+        }
+    }
+}
+
+// Global average pool, split over channel chunks so the grid fills the machine: block = 64 channels x 4
+// pixel lanes; pooled[b][c] = mean over HW.
+__global__ void __launch_bounds__(256)
+gap_kernel(const float* __restrict__ feat, int HW, int C, float* __restrict__ pooled) {
+    __shared__ float part[4][64];
+    const int b = blockIdx.x, c = blockIdx.y * 64 + (threadIdx.x & 63), pl = threadIdx.x >> 6;
+    float s = 0.f;
+    if (c < C) {
+        const float* f = feat + (size_t)b * HW * C + c;
+        for (int p = pl; p < HW; p += 4) s += f[(size_t)p * C];
+    }
+    part[pl][threadIdx.x & 63] = s;
+    __syncthreads();
+    if (pl == 0 && c < C)
+        pooled[(size_t)b * C + c] = (part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x]) * (1.f / (float)HW);
+}
+
+// out[b][o] = clamp(bias[o] + pooled[b] . w[o]); one warp per output, 8 outputs per block.
+__global__ void __launch_bounds__(256)
+head_linear_kernel(const float* __restrict__ pooled, int C, const float* __restrict__ w, const float* __restrict__ bias,
+                   int n_out, const uint8_t* __restrict__ codes, float* __restrict__ out) {
+    const int b = blockIdx.x, lane = threadIdx.x & 31, o = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (o >= n_out) return;
+    const float* wr = w + (size_t)o * C;
+    const float* pb = pooled + (size_t)b * C;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(pb[c], wr[c], acc);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) {
+        float v = acc + bias[o];
+        int code = codes ? codes[o] : 0;
+        if (code == 1) v = fminf(fmaxf(v, 0.f), 1.f);
+        else if (code == 2) v = fmaxf(v, 0.f);
+        else if (code == 3) v = fminf(fmaxf(v, -0.2f), 0.2f);
+        out[(size_t)b * n_out + o] = v;
     }
 }
 
@@ -261,37 +355,6 @@ conv1x1_sigmoid_kernel(const float* __restrict__ in, int B, int HW, int Cin, con
     }
 }
 
-__global__ void __launch_bounds__(256)
-gap_linear_kernel(const float* __restrict__ feat, int HW, int C, const float* __restrict__ w, const float* __restrict__ bias,
-                  int n_out, const uint8_t* __restrict__ codes, float* __restrict__ out) {
-    extern __shared__ float pooled[];             // [C]
-    const int b = blockIdx.x;
-    const float* f = feat + (size_t)b * HW * C;
-    const float inv = 1.f / (float)HW;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float s = 0.f;
-        for (int p = 0; p < HW; ++p) s += f[(size_t)p * C + c];
-        pooled[c] = s * inv;
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int o = warp; o < n_out; o += nw) {
-        const float* wr = w + (size_t)o * C;
-        float acc = 0.f;
-        for (int c = lane; c < C; c += 32) acc = fmaf(pooled[c], wr[c], acc);
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-        if (lane == 0) {
-            float v = acc + bias[o];
-            int code = codes ? codes[o] : 0;
-            if (code == 1) v = fminf(fmaxf(v, 0.f), 1.f);
-            else if (code == 2) v = fmaxf(v, 0.f);
-            else if (code == 3) v = fminf(fmaxf(v, -0.2f), 0.2f);
-            out[(size_t)b * n_out + o] = v;
-        }
-    }
-}
-
 }  // namespace
 
 int conv_gemm(const ConvProblem& p, cudaStream_t st) {
@@ -323,13 +386,17 @@ static inline int same_pad_begin(int H, int stride) {
 }
 
 int dwconv3x3(const float* in, int B, int H, int W, int C, int stride, const float* w9c, const float* scale,
-              const float* bias, float* out, cudaStream_t st) {
+              const float* bias, float* out, cudaStream_t st, bool round_out) {
     SMK_REQUIRE(C % 4 == 0, "dwconv3x3: C must be a multiple of 4");
     int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
-    long total = (long)B * Ho * Wo * (C / 4);
-    int blocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
+    SMK_REQUIRE(stride == 1 || stride == 2, "dwconv3x3: stride must be 1 or 2");
+    long total = (long)B * Ho * ((Wo + 3) / 4) * (C / 4);
+    int blocks = (int)std::min<long>((total + 255) / 256, 148L * 32);
     SMK_TAG("dwconv3x3", 4.0 * ((double)B * H * W * C + (double)B * Ho * Wo * C + 11.0 * C), 18.0 * B * Ho * Wo * C, st);
-    dwconv3x3_kernel<<<blocks, 256, 0, st>>>(in, B, H, W, C, stride, same_pad_begin(H, stride), Ho, Wo, w9c, scale, bias, out);
+    if (stride == 1)
+        dwconv3x3_px4_kernel<1><<<blocks, 256, 0, st>>>(in, B, H, W, C, same_pad_begin(H, 1), Ho, Wo, w9c, scale, bias, out, round_out ? 1 : 0);
+    else
+        dwconv3x3_px4_kernel<2><<<blocks, 256, 0, st>>>(in, B, H, W, C, same_pad_begin(H, 2), Ho, Wo, w9c, scale, bias, out, round_out ? 1 : 0);
     SMK_CHECK_LAUNCH();
     return 0;
 }
@@ -370,9 +437,12 @@ int conv1x1_sigmoid_nchw(const float* in, int B, int HW, int Cin, const float* w
 }
 
 int gap_linear(const float* feat, int B, int HW, int C, const float* w, const float* bias, int n_out, const uint8_t* codes,
-               float* out, cudaStream_t st) {
-    SMK_TAG("gap_linear", 4.0 * ((double)B * HW * C + (double)n_out * C + (double)B * n_out), 2.0 * (double)B * C * (HW + n_out), st);
-    gap_linear_kernel<<<B, 256, (size_t)C * 4, st>>>(feat, HW, C, w, bias, n_out, codes, out);
+               float* pooled_scratch, float* out, cudaStream_t st) {
+    SMK_TAG("gap_pool", 4.0 * ((double)B * HW * C + (double)B * C), (double)B * C * HW, st);
+    gap_kernel<<<dim3(B, cdiv(C, 64)), 256, 0, st>>>(feat, HW, C, pooled_scratch);
+    SMK_CHECK_LAUNCH();
+    SMK_TAG("head_linear", 4.0 * ((double)B * C + (double)n_out * C + (double)B * n_out), 2.0 * (double)B * C * n_out, st);
+    head_linear_kernel<<<dim3(B, cdiv(n_out, 8)), 256, 0, st>>>(pooled_scratch, C, w, bias, n_out, codes, out);
     SMK_CHECK_LAUNCH();
     return 0;
 }

@@ -24,13 +24,14 @@ struct ConvProblem {
     const float* res; int ld_res;        // optional residual added after scale/bias (no ReLU afterwards)
     float* out; int ld_out;              // pixel stride of the output (>= N; lets us write a concat slice)
     int shuffle;                         // 1: n = (dy*2+dx)*Cout + co  ->  pixel (2h+dy, 2w+dx), channel co
+    int round_out;                       // 1: round outputs to TF32 (they feed a tensor-core layer)
 };
 
 int conv_gemm(const ConvProblem& p, cudaStream_t st);
 
 // Depthwise 3x3, TF-"SAME" padding (pad_beg = pad_total/2), stride 1 or 2, fused scale/bias/ReLU.
 int dwconv3x3(const float* in, int B, int H, int W, int C, int stride, const float* w9c /*[9][C]*/,
-              const float* scale, const float* bias, float* out, cudaStream_t st);
+              const float* scale, const float* bias, float* out, cudaStream_t st, bool round_out = false);
 // Stem: NCHW fp32 image -> NHWC, 3x3 stride 2 TF-SAME, Cout = 16, fused scale/bias/ReLU.
 int stem_conv(const float* img_nchw, int B, int H, int W, const float* w /*[27][16]*/, const float* scale,
               const float* bias, float* out, cudaStream_t st);
@@ -42,6 +43,6 @@ int conv1x1_sigmoid_nchw(const float* in, int B, int HW, int Cin, const float* w
 // Global average pool over HW pixels + Linear(C -> n_out); clamp codes per output column:
 //   0 none, 1 clamp[0,1], 2 relu, 3 clamp[-0.2,0.2]
 int gap_linear(const float* feat, int B, int HW, int C, const float* w /*[n_out][C]*/, const float* bias, int n_out,
-               const uint8_t* clamp_codes /*device, may be null*/, float* out, cudaStream_t st);
+               const uint8_t* clamp_codes /*device, may be null*/, float* pooled_scratch /*[B][C]*/, float* out, cudaStream_t st);
 
 }  // namespace smk

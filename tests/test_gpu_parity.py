@@ -254,3 +254,42 @@ def test_generator_batch_independence(generator):
     a = generator(x)
     b = generator(x[3:5].contiguous())
     rel_close(b, a[3:5], 1e-5, 1e-6)
+
+
+# ------------------------------------------------------------------------- TF32 tensor-core precision
+# precision = 1 runs the 1x1 / 3x3 / transposed convolutions on tcgen05 with TF32 operands (10-bit
+# mantissa, fp32 accumulate) — the arithmetic the reference itself gets from cuDNN on Ampere+ GPUs
+# (torch.backends.cudnn.allow_tf32 defaults to True).  Tolerance: 5e-3 of the output scale through
+# the ~50-layer encoder and the 27-conv generator, stated here; the fp32 path above stays at 1e-4.
+def test_generator_tf32_tensor_core_path(generator, golden):
+    import copy
+    from oracle import generator_ref
+    gtc = copy.deepcopy(generator)
+    gtc.precision = 1
+    r = golden("render")
+    x2 = torch.cat([T(r["rendered_img"]), synth_inputs.masked_images(2, 302)], 1)
+    ref = generator_ref.generator_forward_ref({k: v.cpu() for k, v in generator.state_dict().items()}, x2)
+    y = gtc(x2.to(DEV))
+    assert torch.isfinite(y).all()
+    err = rel_close(y, ref, 5e-3, 0)
+    y32 = generator(x2.to(DEV))
+    rel_close(y, y32, 5e-3, 0)
+    x = torch.cat([synth_inputs.images(5, 305), synth_inputs.masked_images(5, 306)], 1).to(DEV)   # 5*196 rows: ragged tiles
+    a = gtc(x)
+    rel_close(gtc(x[1:3].contiguous()), a[1:3], 1e-6, 1e-7)        # tile boundaries do not leak across images
+    rel_close(a, generator(x), 5e-3, 0)
+
+
+def test_encoder_tf32_tensor_core_path(encoder):
+    import copy
+    from oracle import encoder_ref
+    etc = copy.deepcopy(encoder)
+    etc.precision = 1
+    img = synth_inputs.images(5, 402)
+    ref = encoder_ref.encoder_forward_ref({k: v.cpu() for k, v in encoder.state_dict().items()}, img)
+    o = etc(img.to(DEV))
+    for k in o:
+        scale = max(float(ref[k].abs().max()), 1.0)
+        assert float((o[k].cpu() - ref[k]).abs().max()) <= 5e-3 * scale, k
+    o32 = encoder(img.to(DEV))
+    assert float((o["shape_params"] - o32["shape_params"]).abs().max()) > 0      # really a different arithmetic path
