@@ -17,6 +17,16 @@ static std::vector<ProfEntry> g_entries;
 static bool g_prof = false, g_pending = false;
 static cudaStream_t g_pending_stream = nullptr;
 static unsigned long long g_launches = 0;
+bool g_prof_detail = false;          // level 2: GEMM / depthwise launches are tagged with their shape
+
+const char* prof_shape_tag(const char* base, long m, long k, long n) {
+    static std::vector<char*> pool;
+    char buf[96];
+    snprintf(buf, sizeof(buf), "%s:M%ld_K%ld_N%ld", base, m, k, n);
+    for (char* p : pool) if (strcmp(p, buf) == 0) return p;
+    pool.push_back(strdup(buf));
+    return pool.back();
+}
 
 void prof_begin(const char* tag, double bytes, double flops, cudaStream_t st) {
     __atomic_add_fetch(&g_launches, 1ULL, __ATOMIC_RELAXED);
@@ -35,7 +45,7 @@ void prof_end() {
 }  // namespace smk
 
 extern "C" unsigned long long smk_launch_count(void) { return smk::g_launches; }
-extern "C" void smk_profiler_enable(int on) { smk::g_prof = on != 0; }
+extern "C" void smk_profiler_enable(int on) { smk::g_prof = on != 0; smk::g_prof_detail = on >= 2; }
 extern "C" void smk_profiler_reset(void) {
     for (auto& e : smk::g_entries) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     smk::g_entries.clear();

@@ -31,6 +31,8 @@ void set_error(const char* fmt, ...);
 // report per-kernel time, algorithmic bytes and FLOPs without an external profiler.
 void prof_begin(const char* tag, double bytes, double flops, cudaStream_t st);
 void prof_end();
+extern bool g_prof_detail;
+const char* prof_shape_tag(const char* base, long m, long k, long n);   // interned "base:M.._K.._N.."
 #define SMK_TAG(tag, bytes, flops, st) smk::prof_begin(tag, (double)(bytes), (double)(flops), st)
 #define SMK_CHECK_LAUNCH() do { smk::prof_end(); SMK_CHECK_CUDA(cudaGetLastError()); } while (0)
 

@@ -393,7 +393,9 @@ int tc_conv(const TcConv& p, cudaStream_t st) {
     if (int rc = encode_2d(&tmB, p.wt, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, (uint32_t)BN)) return rc;
     {
         const double cin_eff = p.mode == 0 ? p.K : p.Cin;
-        SMK_TAG(p.mode == 0 ? (p.store == 1 ? "upconv_gemm_tc" : "pw_gemm_tc") : "conv3x3_gemm_tc",
+        const char* tag = p.mode == 0 ? (p.store == 1 ? "upconv_gemm_tc" : "pw_gemm_tc") : "conv3x3_gemm_tc";
+        if (g_prof_detail) tag = prof_shape_tag(tag, M, p.K, p.N);
+        SMK_TAG(tag,
                 4.0 * ((double)M * cin_eff + (double)p.K * p.N + (double)M * p.N * (p.res ? 2 : 1) + 2.0 * p.N),
                 2.0 * (double)M * p.N * p.K, st);
     }

@@ -363,7 +363,9 @@ int conv_gemm(const ConvProblem& p, cudaStream_t st) {
     SMK_REQUIRE(p.mode == 0 || p.Cin % 4 == 0, "conv_gemm: Cin must be a multiple of 4");
     {
         const double cin_eff = p.mode == 0 ? p.K : p.Cin;       // unique input bytes (not im2col-expanded)
-        SMK_TAG(p.mode == 0 ? (p.shuffle ? "upconv_gemm_f32" : "pw_gemm_f32") : "conv3x3_gemm_f32",
+        const char* tag = p.mode == 0 ? (p.shuffle ? "upconv_gemm_f32" : "pw_gemm_f32") : "conv3x3_gemm_f32";
+        if (g_prof_detail) tag = prof_shape_tag(tag, M, p.K, p.N);
+        SMK_TAG(tag,
                 4.0 * ((double)M * cin_eff + (double)p.K * p.N + (double)M * p.N * (p.res ? 2 : 1) + 2.0 * p.N),
                 2.0 * (double)M * p.N * p.K, st);
     }
@@ -392,7 +394,7 @@ int dwconv3x3(const float* in, int B, int H, int W, int C, int stride, const flo
     SMK_REQUIRE(stride == 1 || stride == 2, "dwconv3x3: stride must be 1 or 2");
     long total = (long)B * Ho * ((Wo + 3) / 4) * (C / 4);
     int blocks = (int)std::min<long>((total + 255) / 256, 148L * 32);
-    SMK_TAG("dwconv3x3", 4.0 * ((double)B * H * W * C + (double)B * Ho * Wo * C + 11.0 * C), 18.0 * B * Ho * Wo * C, st);
+    SMK_TAG(g_prof_detail ? prof_shape_tag("dwconv3x3", (long)B * Ho * Wo, stride, C) : "dwconv3x3", 4.0 * ((double)B * H * W * C + (double)B * Ho * Wo * C + 11.0 * C), 18.0 * B * Ho * Wo * C, st);
     if (stride == 1)
         dwconv3x3_px4_kernel<1><<<blocks, 256, 0, st>>>(in, B, H, W, C, same_pad_begin(H, 1), Ho, Wo, w9c, scale, bias, out, round_out ? 1 : 0);
     else
