@@ -95,6 +95,12 @@ struct SmkEncoder {
     int n_shape = 300, n_exp = 50, precision = 0;
     size_t max_act = 0;          // floats per image of the largest activation
     smk::DeviceArena arena;
+    cudaStream_t side[2] = {nullptr, nullptr};     // fork/join streams for the two large backbones
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    ~SmkEncoder() {
+        for (int s = 0; s < 2; ++s) { if (side[s]) cudaStreamDestroy(side[s]); if (join[s]) cudaEventDestroy(join[s]); }
+        if (fork) cudaEventDestroy(fork);
+    }
 };
 
 extern "C" int smk_encoder_create(const SmkEncoderDesc* desc, SmkEncoder** out) {
@@ -153,6 +159,12 @@ extern "C" int smk_encoder_create(const SmkEncoderDesc* desc, SmkEncoder** out) 
         }
         if (e != cudaSuccess) { smk::set_error("smk_encoder_create: upload failed: %s", cudaGetErrorString(e)); delete h; return (int)e; }
     }
+    for (int s = 0; s < 2 && e == cudaSuccess; ++s) {
+        e = cudaStreamCreateWithFlags(&h->side[s], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->join[s], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming);
+    if (e != cudaSuccess) { smk::set_error("smk_encoder_create: stream/event creation failed: %s", cudaGetErrorString(e)); delete h; return (int)e; }
     *out = h;
     return 0;
 }
@@ -160,7 +172,7 @@ extern "C" int smk_encoder_create(const SmkEncoderDesc* desc, SmkEncoder** out) 
 extern "C" void smk_encoder_destroy(SmkEncoder* h) { delete h; }
 
 extern "C" size_t smk_encoder_workspace_bytes(const SmkEncoder* h, int B) {
-    return 4 * smk::ws_round((size_t)B * h->max_act * sizeof(float));
+    return 12 * smk::ws_round((size_t)B * h->max_act * sizeof(float));      // 4 buffers per backbone, 3 concurrent backbones
 }
 
 static int pointwise(const ConvW& c, const float* in, int B, int H, int W, bool relu, const float* res, float* out, cudaStream_t st) {
@@ -184,13 +196,22 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
     SMK_REQUIRE(h && img && pose_cam && shape && expr, "smk_encoder_forward: null argument");
     SMK_REQUIRE(B > 0, "smk_encoder_forward: negative batch");
     SMK_REQUIRE(ws && ws_bytes >= smk_encoder_workspace_bytes(h, B), "smk_encoder_forward: workspace too small");
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t main_st = (cudaStream_t)stream;
     smk::Workspace w(ws, ws_bytes);
-    float* buf[4];
-    for (int i = 0; i < 4; ++i) buf[i] = w.take<float>((size_t)B * h->max_act);
+    float* bufs[3][4];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 4; ++j) bufs[i][j] = w.take<float>((size_t)B * h->max_act);
+    SMK_REQUIRE(bufs[2][3] != nullptr, "smk_encoder_forward: workspace carve-up failed");
     float* outs[3] = {pose_cam, shape, expr};
+    // The three backbones are independent (smirk_encoder.py:123-133 merely runs them one after another):
+    // fork the two large ones onto the handle's side streams so their many small, latency-bound layers
+    // overlap; join before returning.  Event record/wait on other streams is legal under stream capture,
+    // so a CUDA graph of the caller's stream gets three parallel branches.
+    SMK_CHECK_CUDA(cudaEventRecord(h->fork, main_st));
+    for (int s = 0; s < 2; ++s) SMK_CHECK_CUDA(cudaStreamWaitEvent(h->side[s], h->fork, 0));
     for (int i = 0; i < 3; ++i) {
         const Backbone& bb = h->bb[i];
+        cudaStream_t st = i == 0 ? main_st : h->side[i - 1];
+        float* const* buf = bufs[i];
         float *x = buf[0], *y = buf[1], *e = buf[2], *d = buf[3];
         int rc = smk::stem_conv(img, B, 224, 224, bb.stem.w, bb.stem.scale, bb.stem.bias, x, st);
         if (rc) return rc;
@@ -213,6 +234,10 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
         }
         rc = smk::gap_linear(x, B, res * res, bb.feat, bb.head_w, bb.head_b, bb.n_out, bb.codes, y, outs[i], st);
         if (rc) return rc;
+    }
+    for (int s = 0; s < 2; ++s) {
+        SMK_CHECK_CUDA(cudaEventRecord(h->join[s], h->side[s]));
+        SMK_CHECK_CUDA(cudaStreamWaitEvent(main_st, h->join[s], 0));
     }
     return 0;
 }

@@ -7,10 +7,11 @@
 //                       with shapedirs at create time), Rodrigues (lbs.py:274-305), kinematic chain
 //                       (lbs.py:321-378) in registers, pose feature (lbs.py:197), contour-LUT row
 //                       (FLAME.py:117-159).
-//   flame_verts_kernel  thread = vertex, BT faces per thread in registers; streams the transposed
-//                       shapedirs [350][3V] (coalesced, read once per batch tile), then posedirs,
-//                       then skins with the 5 joint transforms held in shared memory and adds the
-//                       eyelid offsets (FLAME.py:284-286).
+//   flame_verts_kernel  CTA = 32 vertices x 4 k-slices, BT faces per thread in registers; each warp
+//                       streams its quarter of the transposed shapedirs [350][3V] and posedirs
+//                       (384 contiguous bytes per load), partial sums meet in shared memory, then
+//                       the vertices are skinned with the 5 joint transforms held in shared memory
+//                       and the eyelid offsets are added (FLAME.py:284-286).
 //   flame_landmarks_kernel  241 barycentric gathers per face (lbs.py:101-137).
 #include "common.cuh"
 #include <math.h>
@@ -165,51 +166,68 @@ flame_verts_kernel(FlameDev d, const float* __restrict__ betas, const float* __r
     if (tid < BT * 2) sE[tid] = eyelid ? eyelid[(size_t)min(b0 + tid / 2, B - 1) * 2 + (tid & 1)] : 0.f;
     __syncthreads();
 
-    const int v = blockIdx.x * 128 + tid;
-    if (v >= d.V) return;
-    const int m = 3 * v;
+    // CTA = 32 vertices x 4 k-slices: warp ks accumulates its quarter of the 350 shape and 36 pose
+    // directions for the warp's 32 vertices (each global load is 384 contiguous bytes), partial sums
+    // meet in shared memory, then warp ks finishes face t = ks (, ks+4 ...) of the batch tile.
+    const int vl = tid & 31, ks = tid >> 5;
+    const int v = blockIdx.x * 32 + vl;
+    const bool v_ok = v < d.V;
+    const int m = 3 * (v_ok ? v : 0);
     float acc[BT][3];
-    {
-        float t0 = d.vt[m], t1 = d.vt[m + 1], t2 = d.vt[m + 2];
 #pragma unroll
-        for (int t = 0; t < BT; ++t) { acc[t][0] = t0; acc[t][1] = t1; acc[t][2] = t2; }
-    }
-    // v_shaped = v_template + shapedirs . beta                                    lbs.py:184,270
-    const float* sd = d.sdt + m;
+    for (int t = 0; t < BT; ++t) { acc[t][0] = 0.f; acc[t][1] = 0.f; acc[t][2] = 0.f; }
     const size_t Mp = d.Mp;
-#pragma unroll 4
-    for (int l = 0; l < d.L; ++l) {
-        float s0 = __ldg(sd + l * Mp), s1 = __ldg(sd + l * Mp + 1), s2 = __ldg(sd + l * Mp + 2);
+    {   // v_shaped - v_template = shapedirs . beta                                 lbs.py:184,270
+        const int per = (d.L + 3) >> 2, l0 = ks * per, l1 = min(d.L, l0 + per);
+        const float* sd = d.sdt + m;
+#pragma unroll 8
+        for (int l = l0; l < l1; ++l) {
+            float s0 = __ldg(sd + l * Mp), s1 = __ldg(sd + l * Mp + 1), s2 = __ldg(sd + l * Mp + 2);
 #pragma unroll
-        for (int t = 0; t < BT; ++t) {
-            float be = sB[l * BT + t];
-            acc[t][0] = fmaf(s0, be, acc[t][0]);
-            acc[t][1] = fmaf(s1, be, acc[t][1]);
-            acc[t][2] = fmaf(s2, be, acc[t][2]);
+            for (int t = 0; t < BT; ++t) {
+                float be = sB[l * BT + t];
+                acc[t][0] = fmaf(s0, be, acc[t][0]);
+                acc[t][1] = fmaf(s1, be, acc[t][1]);
+                acc[t][2] = fmaf(s2, be, acc[t][2]);
+            }
+        }
+        // + pose_feature . posedirs                                                lbs.py:199-208
+        const float* pd = d.pdt + m;
+#pragma unroll
+        for (int p = ks * 9; p < ks * 9 + 9; ++p) {
+            float s0 = __ldg(pd + p * Mp), s1 = __ldg(pd + p * Mp + 1), s2 = __ldg(pd + p * Mp + 2);
+#pragma unroll
+            for (int t = 0; t < BT; ++t) {
+                float f = sP[p * BT + t];
+                acc[t][0] = fmaf(s0, f, acc[t][0]);
+                acc[t][1] = fmaf(s1, f, acc[t][1]);
+                acc[t][2] = fmaf(s2, f, acc[t][2]);
+            }
         }
     }
-    // v_posed = v_shaped + pose_feature . posedirs                                lbs.py:199-208
-    const float* pd = d.pdt + m;
-#pragma unroll 4
-    for (int p = 0; p < kPF; ++p) {
-        float s0 = __ldg(pd + p * Mp), s1 = __ldg(pd + p * Mp + 1), s2 = __ldg(pd + p * Mp + 2);
+    float* sPart = sE + BT * 2;                     // [4 slices][BT][3][32 lanes]
 #pragma unroll
-        for (int t = 0; t < BT; ++t) {
-            float f = sP[p * BT + t];
-            acc[t][0] = fmaf(s0, f, acc[t][0]);
-            acc[t][1] = fmaf(s1, f, acc[t][1]);
-            acc[t][2] = fmaf(s2, f, acc[t][2]);
-        }
-    }
+    for (int t = 0; t < BT; ++t)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sPart[((ks * BT + t) * 3 + k) * 32 + vl] = acc[t][k];
+    __syncthreads();
+    if (!v_ok) return;
     // skinning: T = sum_j w_j A_j ; out = T [v_posed;1]                           lbs.py:214-225
     float w[kJ];
 #pragma unroll
     for (int j = 0; j < kJ; ++j) w[j] = __ldg(d.wt + (size_t)j * d.V + v);
     const float le0 = d.leye[m], le1 = d.leye[m + 1], le2 = d.leye[m + 2];
     const float re0 = d.reye[m], re1 = d.reye[m + 1], re2 = d.reye[m + 2];
-#pragma unroll
-    for (int t = 0; t < BT; ++t) {
+    const float t0 = d.vt[m], t1 = d.vt[m + 1], t2 = d.vt[m + 2];
+    for (int t = ks; t < BT; t += 4) {
         if (b0 + t >= B) break;
+        float x = t0, y = t1, z = t2;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            x += sPart[((q * BT + t) * 3 + 0) * 32 + vl];
+            y += sPart[((q * BT + t) * 3 + 1) * 32 + vl];
+            z += sPart[((q * BT + t) * 3 + 2) * 32 + vl];
+        }
         float T[12];
 #pragma unroll
         for (int e = 0; e < 12; ++e) {
@@ -218,7 +236,6 @@ flame_verts_kernel(FlameDev d, const float* __restrict__ betas, const float* __r
             for (int j = 0; j < kJ; ++j) a = fmaf(w[j], sA[t * 60 + j * 12 + e], a);
             T[e] = a;
         }
-        float x = acc[t][0], y = acc[t][1], z = acc[t][2];
         float ox = T[0] * x + T[1] * y + T[2] * z + T[3];
         float oy = T[4] * x + T[5] * y + T[6] * z + T[7];
         float oz = T[8] * x + T[9] * y + T[10] * z + T[11];
@@ -329,7 +346,7 @@ extern "C" size_t smk_flame_workspace_bytes(const SmkFlame*, int B) {
 template <int BT>
 static int launch_verts(const FlameDev& d, const float* betas, const float* eyelid, const float* A, const float* pf,
                         int B, float* verts, cudaStream_t st) {
-    size_t smem = ((size_t)d.L * BT + kPF * BT + BT * 60 + BT * 2) * sizeof(float);
+    size_t smem = ((size_t)d.L * BT + kPF * BT + BT * 60 + BT * 2 + 4 * BT * 3 * 32) * sizeof(float);
     if (smem > 48 * 1024)
         SMK_CHECK_CUDA(cudaFuncSetAttribute(flame_verts_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(smk::cdiv(d.V, 128), smk::cdiv(B, BT));

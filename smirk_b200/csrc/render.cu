@@ -142,19 +142,31 @@ raster_tile_kernel(RenderDev d, const float* __restrict__ recs, const uint32_t* 
     if (tid == 0) s_count = 0;
     __syncthreads();
     // -- bin: compact the ids of triangles whose conservative tile range covers this tile
-    const uint32_t* rg = ranges + (size_t)b * d.F;
-    for (int base = 0; base < d.F; base += nthr) {
-        int f = base + tid;
-        bool hit = false;
-        if (f < d.F) {
-            uint32_t c = rg[f];
-            hit = (c & 0xFF) <= tx && tx <= ((c >> 8) & 0xFF) && ((c >> 16) & 0xFF) <= ty && ty <= (c >> 24);
+    //    (4 packed ranges per thread per pass: one 16-byte load, one shared atomic per warp)
+    const uint4* rg4 = reinterpret_cast<const uint4*>(ranges + (size_t)b * d.F);
+    const int F4 = d.F >> 2;                                  // F % 4 == 0 is checked at create time
+    for (int base = 0; base < F4; base += nthr) {
+        const int i4 = base + tid;
+        uint32_t c[4] = {0xFFu, 0xFFu, 0xFFu, 0xFFu};
+        if (i4 < F4) { uint4 v = __ldg(rg4 + i4); c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w; }
+        unsigned hits = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            bool hit = (c[k] & 0xFF) <= tx && tx <= ((c[k] >> 8) & 0xFF) && ((c[k] >> 16) & 0xFF) <= ty && ty <= (c[k] >> 24);
+            hits |= (hit ? 1u : 0u) << k;
         }
-        unsigned m = __ballot_sync(0xffffffffu, hit);
-        int lane = tid & 31, wbase = 0;
-        if (lane == 0 && m) wbase = atomicAdd(&s_count, __popc(m));
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (hit) s_cand[wbase + __popc(m & ((1u << lane) - 1))] = (uint16_t)f;
+        const int lane = tid & 31;
+        const int mine = __popc(hits);
+        int incl = mine;                                      // inclusive warp scan of the per-lane hit counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int wbase = 0;
+        if (lane == 31 && total) wbase = atomicAdd(&s_count, total);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        int pos = wbase + incl - mine;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (hits & (1u << k)) s_cand[pos++] = (uint16_t)(i4 * 4 + k);
     }
     __syncthreads();
     const int ncand = s_count;
@@ -238,7 +250,8 @@ extern "C" int smk_renderer_create(const SmkRendererDesc* desc, SmkRenderer** ou
     SMK_REQUIRE(desc && out && desc->mask_ids && desc->faces, "smk_renderer_create: null argument");
     SMK_REQUIRE(desc->image_size > 0 && desc->image_size % TILE_W == 0 && desc->image_size % TILE_H == 0 &&
                 desc->image_size / TILE_H < 255, "smk_renderer_create: image_size must be a multiple of 32 (got %d)", desc->image_size);
-    SMK_REQUIRE(desc->n_faces > 0 && desc->n_faces < 65536, "smk_renderer_create: n_faces must be in (0, 65536)");
+    SMK_REQUIRE(desc->n_faces > 0 && desc->n_faces < 65536 && desc->n_faces % 4 == 0,
+                "smk_renderer_create: n_faces must be in (0, 65536) and a multiple of 4 (got %d)", desc->n_faces);
     SmkRenderer* h = new SmkRenderer();
     RenderDev& d = h->d;
     d.V = desc->n_verts; d.NM = desc->n_mask; d.F = desc->n_faces; d.S = desc->image_size;
