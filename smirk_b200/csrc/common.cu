@@ -37,6 +37,7 @@ void prof_begin(const char* tag, double bytes, double flops, cudaStream_t st) {
     g_entries.push_back(e);
     g_pending = true; g_pending_stream = st;
 }
+bool profiling() { return g_prof; }
 void prof_end() {
     if (!g_prof || !g_pending) return;
     cudaEventRecord(g_entries.back().b, g_pending_stream);

@@ -32,6 +32,7 @@ void set_error(const char* fmt, ...);
 void prof_begin(const char* tag, double bytes, double flops, cudaStream_t st);
 void prof_end();
 extern bool g_prof_detail;
+bool profiling();                      // true while the event profiler is on (callers then serialise side streams)
 const char* prof_shape_tag(const char* base, long m, long k, long n);   // interned "base:M.._K.._N.."
 #define SMK_TAG(tag, bytes, flops, st) smk::prof_begin(tag, (double)(bytes), (double)(flops), st)
 #define SMK_CHECK_LAUNCH() do { smk::prof_end(); SMK_CHECK_CUDA(cudaGetLastError()); } while (0)

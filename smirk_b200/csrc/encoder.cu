@@ -206,11 +206,14 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
     // fork the two large ones onto the handle's side streams so their many small, latency-bound layers
     // overlap; join before returning.  Event record/wait on other streams is legal under stream capture,
     // so a CUDA graph of the caller's stream gets three parallel branches.
-    SMK_CHECK_CUDA(cudaEventRecord(h->fork, main_st));
-    for (int s = 0; s < 2; ++s) SMK_CHECK_CUDA(cudaStreamWaitEvent(h->side[s], h->fork, 0));
+    const bool concurrent = !smk::profiling();   // the event profiler wants one kernel at a time
+    if (concurrent) {
+        SMK_CHECK_CUDA(cudaEventRecord(h->fork, main_st));
+        for (int s = 0; s < 2; ++s) SMK_CHECK_CUDA(cudaStreamWaitEvent(h->side[s], h->fork, 0));
+    }
     for (int i = 0; i < 3; ++i) {
         const Backbone& bb = h->bb[i];
-        cudaStream_t st = i == 0 ? main_st : h->side[i - 1];
+        cudaStream_t st = (i == 0 || !concurrent) ? main_st : h->side[i - 1];
         float* const* buf = bufs[i];
         float *x = buf[0], *y = buf[1], *e = buf[2], *d = buf[3];
         int rc = smk::stem_conv(img, B, 224, 224, bb.stem.w, bb.stem.scale, bb.stem.bias, x, st);
@@ -235,7 +238,7 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
         rc = smk::gap_linear(x, B, res * res, bb.feat, bb.head_w, bb.head_b, bb.n_out, bb.codes, y, outs[i], st);
         if (rc) return rc;
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 2 && concurrent; ++s) {
         SMK_CHECK_CUDA(cudaEventRecord(h->join[s], h->side[s]));
         SMK_CHECK_CUDA(cudaStreamWaitEvent(main_st, h->join[s], 0));
     }

@@ -349,7 +349,7 @@ static int launch_verts(const FlameDev& d, const float* betas, const float* eyel
     size_t smem = ((size_t)d.L * BT + kPF * BT + BT * 60 + BT * 2 + 4 * BT * 3 * 32) * sizeof(float);
     if (smem > 48 * 1024)
         SMK_CHECK_CUDA(cudaFuncSetAttribute(flame_verts_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(smk::cdiv(d.V, 128), smk::cdiv(B, BT));
+    dim3 grid(smk::cdiv(d.V, 32), smk::cdiv(B, BT));          // 32 vertices x 4 k-slices per CTA
     SMK_TAG("flame_verts", 4.0 * ((double)(d.L + kPF) * d.Mp + 6.0 * d.Mp + 5.0 * d.V + (double)B * (d.L + 3.0 * d.V + 98)),
             2.0 * B * (3.0 * d.V * (d.L + kPF) + (double)d.V * (60 + 12 + 6)), st);
     flame_verts_kernel<BT><<<grid, 128, smem, st>>>(d, betas, eyelid, A, pf, B, verts);
