@@ -312,7 +312,16 @@ def main():
             roof = {"bound": "tensor", "achieved": top["tflops"], "peak": peaks["tensor"], "unit": "TFLOP/s"}
         else:
             roof = {"bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s"}
-        roof.update(frac=roof["achieved"] / roof["peak"], traffic=None, kernel=top_tag, share_of_step=top["share"],
+        # DRAM traffic per launch of that kernel from the committed ncu capture of this same workload
+        # (profiles/*ncu_dram_traffic*.json: dram__bytes_read.sum + dram__bytes_write.sum); null if the
+        # capture does not cover this configuration.
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_ncu_dram_traffic_c2_b32.json")
+        if os.path.exists(tpath) and B == 32 and gen is None and args.precision == "tf32":
+            tk = json.load(open(tpath)).get("kernels", {}).get(top_tag.split(":")[0])
+            if tk:
+                traffic = tk["traffic_bytes_per_launch"]
+        roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, kernel=top_tag, share_of_step=top["share"],
                     launches_per_step=top["launches"] / NP, us_per_launch=top["ms_per_launch"] * 1e3,
                     peak_source=peaks["source"],
                     algorithmic_bytes_per_launch=top["bytes"] / top["launches"],

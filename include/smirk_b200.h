@@ -169,6 +169,12 @@ int smk_debug_conv_tc(const float* in, int ld_in, int B, int H, int W, int Cin, 
                       const float* bias, int N, int K, int mode, int relu, const float* res, int ld_res, int res_pad,
                       float* out, int ld_out, int store, void* stream);
 int smk_debug_reflect_halo(float* buf, int B, int H, int W, int C, void* stream);
+/*   smk_debug_xdw: fused expand-1x1 (TF32 tcgen05) + BN + ReLU + depthwise-3x3 (fp32) + BN + ReLU of a
+ *                  MobileNetV3 inverted-residual block.  x [B,H,W,Cin] NHWC; w1t [mid][Cin]; wdw [9][mid];
+ *                  out [B,ceil(H/stride),ceil(W/stride),mid]; TF-SAME padding.                            */
+int smk_debug_xdw(const float* x, int B, int H, int W, int Cin, const float* w1t, const float* scale1, const float* bias1,
+                  int mid, const float* wdw, const float* scale2, const float* bias2, int stride, int round_out,
+                  float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@
 // scale/bias applied in each convolution's epilogue; activations live in NHWC fp32.
 #include "nn_kernels.cuh"
 #include "gemm_tc.cuh"
+#include "xdw_tc.cuh"
 #include <math.h>
 
 namespace {
@@ -94,6 +95,7 @@ struct SmkEncoder {
     Backbone bb[3];
     int n_shape = 300, n_exp = 50, precision = 0;
     size_t max_act = 0;          // floats per image of the largest activation
+    bool fuse_xdw = false;       // precision 2: inverted-residual blocks use the fused expand+depthwise kernel
     smk::DeviceArena arena;
     cudaStream_t side[2] = {nullptr, nullptr};     // fork/join streams for the two large backbones
     cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
@@ -105,11 +107,12 @@ struct SmkEncoder {
 
 extern "C" int smk_encoder_create(const SmkEncoderDesc* desc, SmkEncoder** out) {
     SMK_REQUIRE(desc && out, "smk_encoder_create: null argument");
-    SMK_REQUIRE(desc->precision == 0 || desc->precision == 1, "smk_encoder_create: precision must be 0 (fp32) or 1 (tf32 tcgen05 1x1 convs)");
-    if (desc->precision == 1) { if (int rc = smk::tc_init()) return rc; }
-    const bool tc = desc->precision == 1;
+    SMK_REQUIRE(desc->precision >= 0 && desc->precision <= 2,
+                "smk_encoder_create: precision must be 0 (fp32), 1 (tf32 tcgen05 1x1 convs) or 2 (1 + fused expand/depthwise blocks)");
+    if (desc->precision >= 1) { if (int rc = smk::tc_init()) return rc; }
+    const bool tc = desc->precision >= 1;
     SmkEncoder* h = new SmkEncoder();
-    h->n_shape = desc->n_shape; h->n_exp = desc->n_exp; h->precision = desc->precision;
+    h->n_shape = desc->n_shape; h->n_exp = desc->n_exp; h->precision = tc ? 1 : 0; h->fuse_xdw = desc->precision == 2;
     const int n_outs[3] = {6, desc->n_shape, desc->n_exp + 5};
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < 3; ++i) {
@@ -225,8 +228,16 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
                 rc = smk::dwconv3x3(x, B, res, res, b.cin, b.stride, b.dw.w, b.dw.scale, b.dw.bias, d, st, h->precision == 1);
                 if (!rc) rc = pointwise(b.pw, d, B, ro, ro, false, b.skip ? x : nullptr, y, st);
             } else if (b.kind == IR) {
-                rc = pointwise(b.pw, x, B, res, res, true, nullptr, e, st);
-                if (!rc) rc = smk::dwconv3x3(e, B, res, res, b.mid, b.stride, b.dw.w, b.dw.scale, b.dw.bias, d, st, h->precision == 1);
+                if (h->fuse_xdw && b.pw.wt) {
+                    // expand 1x1 + depthwise 3x3 in one kernel: the expanded tensor never leaves the SM
+                    smk::XdwConv q{};
+                    q.x = x; q.B = B; q.H = res; q.W = res; q.Cin = b.cin; q.w1t = b.pw.wt; q.scale1 = b.pw.scale; q.bias1 = b.pw.bias;
+                    q.mid = b.mid; q.wdw = b.dw.w; q.scale2 = b.dw.scale; q.bias2 = b.dw.bias; q.stride = b.stride; q.round_out = 1; q.out = d;
+                    rc = smk::xdw_conv(q, st);
+                } else {
+                    rc = pointwise(b.pw, x, B, res, res, true, nullptr, e, st);
+                    if (!rc) rc = smk::dwconv3x3(e, B, res, res, b.mid, b.stride, b.dw.w, b.dw.scale, b.dw.bias, d, st, h->precision == 1);
+                }
                 if (!rc) rc = pointwise(b.pwl, d, B, ro, ro, false, b.skip ? x : nullptr, y, st);
             } else {
                 rc = pointwise(b.pw, x, B, res, res, true, nullptr, y, st);

@@ -1,0 +1,354 @@
+// Fused "expand 1x1 conv + BN + ReLU  ->  depthwise 3x3 conv + BN + ReLU" for MobileNetV3 inverted-residual
+// blocks (reference src/smirk_encoder.py:7-12 -> timm InvertedResidual.conv_pw/bn1/conv_dw/bn2).
+//
+// The expanded tensor e = ReLU(BN(conv_pw(x))) is the largest activation of every block (4-6x the block's
+// input) and in the unfused path is written to HBM by the 1x1 GEMM and read back by the depthwise kernel.
+// Here it only ever exists in TMEM and shared memory:
+//
+//   CTA = one 16x16-pixel window of e for one image (a 14x14 tile of outputs + halo for stride 1, a 7x7
+//         tile for stride 2), looping over the expanded channels in chunks of 64.
+//   warp 0      TMA producer: two 16x8-pixel boxes of x (4-D tiled tensor map over NHWC, halo pixels
+//               outside the image zero-filled by the hardware) + a 64-row box of the 1x1 weights per k-block.
+//   warp 1      tcgen05.mma kind::tf32, M = 2 x 128 window pixels, N = 64 channels, accumulators
+//               double-buffered in TMEM (4 x 64 columns) so chunk c+1 is multiplied while chunk c drains.
+//   warps 2-9   (a) TMEM -> BN1 + ReLU (+ zero outside the image, which is what the depthwise conv's zero
+//               padding of e means) -> shared-memory window E[256][64];
+//               (b) depthwise 3x3 over E on the CUDA cores (float4 over channels), BN2 + ReLU, optional
+//               TF32 rounding, coalesced 256-byte stores of d.
+//
+// Algorithmic HBM traffic per block drops from  x + 2e + d  to  x + d.
+#include "gemm_tc.cuh"
+#include "xdw_tc.cuh"
+#include <cuda.h>
+
+namespace smk {
+namespace {
+
+constexpr int BKB = 128, BK = 32, UMMA_K = 8;
+constexpr int WIN = 16;                         // window edge (pixels of e)
+constexpr int HALF_BYTES = 128 * BKB;           // one 16x8-pixel box, 32 channels: 16 KiB
+constexpr int NC = 64;                          // expanded channels per chunk
+constexpr int B_BYTES = NC * BKB;               // 8 KiB
+constexpr int STAGE_BYTES = 2 * HALF_BYTES + B_BYTES;   // 40 KiB
+constexpr int STAGES = 3;
+constexpr int E_PITCH = NC + 4;                 // floats; 272-byte rows: conflict-free 16-byte column writes
+constexpr int E_BYTES = 256 * E_PITCH * 4;      // 69 632 B
+constexpr int NUM_WORKERS = 256;
+constexpr int NUM_THREADS = 64 + NUM_WORKERS;
+constexpr uint32_t TMEM_COLS = 256;             // (2 buffers) x (2 halves) x 64 columns
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, void* dst, uint64_t* bar, int c, int w, int h, int n) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {          // K-major SWIZZLE_128B, see gemm_tc.cu
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+struct XdwArgs {
+    int H, W, Ho, Wo;              // e (= x) resolution and output resolution
+    int mid, nkb, nchunks;         // expanded channels, 32-wide k-blocks of Cin, 64-wide channel chunks
+    int pad;                       // TF-SAME pad_begin of the depthwise conv (1 for stride 1, 0 for stride 2 on even sizes)
+    int tiles_x, tiles_y;          // output tiles per image
+    const float* scale1; const float* bias1;        // folded BN of the 1x1 conv        [mid]
+    const float* wdw;                               // depthwise weights                 [9][mid]
+    const float* scale2; const float* bias2;        // folded BN of the depthwise conv   [mid]
+    float* out;                                     // d: [B, Ho, Wo, mid]
+    int round_out;
+};
+
+template <int STRIDE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const XdwArgs a) {
+    constexpr int TO = STRIDE == 1 ? 14 : 7;                    // output tile edge
+    constexpr uint32_t IDESC = make_idesc(128, NC);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* E = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + E_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_full = empty + STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int img = blockIdx.z;
+    const int oh0 = blockIdx.y * TO, ow0 = blockIdx.x * TO;
+    const int ey0 = oh0 * STRIDE - a.pad, ex0 = ow0 * STRIDE - a.pad;     // window origin in e / x coordinates
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NUM_WORKERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer: (x window, W1 chunk) per k-block, for every channel chunk =====
+            int it = 0;
+            for (int c = 0; c < a.nchunks; ++c)
+                for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    mbar_expect_tx(&full[s], (uint32_t)STAGE_BYTES);
+                    tma_load_4d(&tmX, st, &full[s], kb * BK, ex0, ey0, img);
+                    tma_load_4d(&tmX, st + HALF_BYTES, &full[s], kb * BK, ex0, ey0 + 8, img);
+                    tma_load_2d(&tmW, st + 2 * HALF_BYTES, &full[s], kb * BK, c * NC);
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            int it = 0;
+            for (int c = 0; c < a.nchunks; ++c) {
+                const int buf = c & 1;
+                mbar_wait(&acc_empty[buf], ((uint32_t)(c >> 1) & 1u) ^ 1u);
+                tcgen05_fence_after();
+                for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    const uint32_t sb = sa + 2 * HALF_BYTES;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half)
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_tf32(tmem_base + (uint32_t)((buf * 2 + half) * NC), make_smem_desc(sa + half * HALF_BYTES + k * UMMA_K * 4),
+                                      make_smem_desc(sb + k * UMMA_K * 4), IDESC, (kb | k) != 0 ? 1u : 0u);
+                    tcgen05_commit(&empty[s]);
+                }
+                tcgen05_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        // ===== workers: 8 warps =====
+        const int wid = warp - 2;                          // 0..7
+        const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
+        const int colh = wid >> 2;                         // which 32 of the chunk's 64 columns (warps {2..5} vs {6..9} cover all quarters)
+        const int t = threadIdx.x - 64;                    // 0..255
+        const int cq = t & 15, slot = t >> 4;              // depthwise role: channel quad within the chunk, output slot
+        for (int c = 0; c < a.nchunks; ++c) {
+            const int buf = c & 1;
+            const int ch0 = c * NC;
+            const int nvalid = min(NC, a.mid - ch0);       // channels of this chunk that exist
+            mbar_wait(&acc_full[buf], (uint32_t)(c >> 1) & 1u);
+            tcgen05_fence_after();
+            // (a) TMEM -> BN1 + ReLU -> E   (rows = window pixels, lane = pixel)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * 2 + half) * NC + colh * 32), v);
+                const int r = quarter * 32 + lane;                       // row within the half: r = hh*16 + ww
+                const int ey = ey0 + half * 8 + (r >> 4), ex = ex0 + (r & 15);
+                const bool inside = ey >= 0 && ey < a.H && ex >= 0 && ex < a.W;
+                float* erow = E + (size_t)(half * 128 + r) * E_PITCH + colh * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int ch = ch0 + colh * 32 + j;
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (inside && colh * 32 + j < nvalid) {
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale1 + ch));
+                        const float4 bi = __ldg(reinterpret_cast<const float4*>(a.bias1 + ch));
+                        o.x = fmaxf(fmaf(v[j], sc.x, bi.x), 0.f); o.y = fmaxf(fmaf(v[j + 1], sc.y, bi.y), 0.f);
+                        o.z = fmaxf(fmaf(v[j + 2], sc.z, bi.z), 0.f); o.w = fmaxf(fmaf(v[j + 3], sc.w, bi.w), 0.f);
+                    }
+                    *reinterpret_cast<float4*>(erow + j) = o;
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);   // this warp has drained its part of the accumulator
+            worker_barrier();
+            // (b) depthwise 3x3 over E: thread = (channel quad, output slot), outputs slot, slot+16, ...
+            if (cq * 4 < nvalid) {
+                const int ch = ch0 + cq * 4;
+                float4 k[9];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) k[q] = __ldg(reinterpret_cast<const float4*>(a.wdw + (size_t)q * a.mid + ch));
+                const float4 s2 = __ldg(reinterpret_cast<const float4*>(a.scale2 + ch));
+                const float4 b2 = __ldg(reinterpret_cast<const float4*>(a.bias2 + ch));
+                for (int p = slot; p < TO * TO; p += 16) {
+                    const int oy = p / TO, ox = p - oy * TO;
+                    const int oh = oh0 + oy, ow = ow0 + ox;
+                    if (oh >= a.Ho || ow >= a.Wo) continue;
+                    const float* e0 = E + (size_t)((oy * STRIDE) * WIN + ox * STRIDE) * E_PITCH + cq * 4;
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const float4 x = *reinterpret_cast<const float4*>(e0 + (size_t)(ky * WIN + kx) * E_PITCH);
+                            const float4 kk = k[ky * 3 + kx];
+                            acc.x = fmaf(x.x, kk.x, acc.x); acc.y = fmaf(x.y, kk.y, acc.y);
+                            acc.z = fmaf(x.z, kk.z, acc.z); acc.w = fmaf(x.w, kk.w, acc.w);
+                        }
+                    float4 o;
+                    o.x = fmaxf(fmaf(acc.x, s2.x, b2.x), 0.f); o.y = fmaxf(fmaf(acc.y, s2.y, b2.y), 0.f);
+                    o.z = fmaxf(fmaf(acc.z, s2.z, b2.z), 0.f); o.w = fmaxf(fmaf(acc.w, s2.w, b2.w), 0.f);
+                    if (a.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                    *reinterpret_cast<float4*>(a.out + (((size_t)img * a.Ho + oh) * a.Wo + ow) * a.mid + ch) = o;
+                }
+            }
+            worker_barrier();                              // E is free for the next chunk
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int load_encoder() {
+    if (g_encode) return 0;
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    SMK_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    SMK_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = (EncodeTiledFn)fn;
+    return 0;
+}
+
+}  // namespace
+
+int xdw_conv(const XdwConv& p, cudaStream_t st) {
+    if (int rc = load_encoder()) return rc;
+    SMK_REQUIRE(p.stride == 1 || p.stride == 2, "xdw_conv: stride must be 1 or 2");
+    SMK_REQUIRE(p.Cin % 4 == 0 && p.mid % 4 == 0, "xdw_conv: Cin and mid must be multiples of 4");
+    SMK_REQUIRE(p.stride == 1 || (p.H % 2 == 0 && p.W % 2 == 0), "xdw_conv: stride 2 expects even input sizes (TF-SAME pad_begin 0)");
+    const int Ho = (p.H + p.stride - 1) / p.stride, Wo = (p.W + p.stride - 1) / p.stride;
+    const int TO = p.stride == 1 ? 14 : 7;
+    CUtensorMap tmX, tmW;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+        cuuint64_t strides[3] = {(cuuint64_t)p.Cin * 4, (cuuint64_t)p.W * p.Cin * 4, (cuuint64_t)p.H * p.W * p.Cin * 4};
+        cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)WIN, 8, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = g_encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p.x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SMK_REQUIRE(r == CUDA_SUCCESS, "xdw_conv: cuTensorMapEncodeTiled(x) failed (%d): B=%d H=%d W=%d Cin=%d", (int)r, p.B, p.H, p.W, p.Cin);
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)p.mid};
+        cuuint64_t strides[1] = {(cuuint64_t)p.Cin * 4};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)NC};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = g_encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p.w1t, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SMK_REQUIRE(r == CUDA_SUCCESS, "xdw_conv: cuTensorMapEncodeTiled(w1) failed (%d): mid=%d Cin=%d", (int)r, p.mid, p.Cin);
+    }
+    XdwArgs a{};
+    a.H = p.H; a.W = p.W; a.Ho = Ho; a.Wo = Wo; a.mid = p.mid; a.nkb = cdiv(p.Cin, BK); a.nchunks = cdiv(p.mid, NC);
+    a.pad = p.stride == 1 ? 1 : 0;
+    a.tiles_x = cdiv(Wo, TO); a.tiles_y = cdiv(Ho, TO);
+    a.scale1 = p.scale1; a.bias1 = p.bias1; a.wdw = p.wdw; a.scale2 = p.scale2; a.bias2 = p.bias2; a.out = p.out; a.round_out = p.round_out;
+    constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + E_BYTES + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    {
+        const double px_in = (double)p.B * p.H * p.W, px_out = (double)p.B * Ho * Wo;
+        const char* tag = "xdw_fused_tc";
+        if (g_prof_detail) tag = prof_shape_tag(tag, (long)px_out, p.Cin, p.mid);
+        SMK_TAG(tag, 4.0 * (px_in * p.Cin + px_out * p.mid + (double)p.mid * (p.Cin + 13)), 2.0 * px_in * p.Cin * p.mid + 18.0 * px_out * p.mid, st);
+    }
+    dim3 grid(a.tiles_x, a.tiles_y, p.B);
+    if (p.stride == 1) xdw_kernel<1><<<grid, NUM_THREADS, smem, st>>>(tmX, tmW, a);
+    else xdw_kernel<2><<<grid, NUM_THREADS, smem, st>>>(tmX, tmW, a);
+    SMK_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace smk
+
+extern "C" int smk_debug_xdw(const float* x, int B, int H, int W, int Cin, const float* w1t, const float* scale1, const float* bias1,
+                             int mid, const float* wdw, const float* scale2, const float* bias2, int stride, int round_out,
+                             float* out, void* stream) {
+    smk::XdwConv p{};
+    p.x = x; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.w1t = w1t; p.scale1 = scale1; p.bias1 = bias1; p.mid = mid; p.wdw = wdw;
+    p.scale2 = scale2; p.bias2 = bias2; p.stride = stride; p.round_out = round_out; p.out = out;
+    return smk::xdw_conv(p, (cudaStream_t)stream);
+}

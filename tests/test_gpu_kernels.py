@@ -177,3 +177,62 @@ def test_conv_tc_store_modes(native_lib):
     got = outp[:, 1:-1, 1:-1].permute(0, 3, 1, 2).cpu()
     assert (got - ref).abs().max() <= 3e-3 * ref.abs().max()
     assert torch.isnan(outp[:, 0]).all() and torch.isnan(outp[:, :, 0]).all()
+
+
+# ------------------------------------------------------------------ fused expand 1x1 + depthwise 3x3
+def tf_same_dw(e, wdw, stride):
+    """Depthwise 3x3 with TF-'SAME' padding (timm pad_type='same'): symmetric for stride 1, bottom/right for stride 2."""
+    C = e.shape[1]
+    if stride == 1:
+        return F.conv2d(e, wdw, padding=1, groups=C)
+    return F.conv2d(F.pad(e, (0, 1, 0, 1)), wdw, stride=2, groups=C)
+
+
+@pytest.mark.parametrize("B,H,Cin,mid,stride", [
+    (2, 28, 40, 120, 1),        # 2x2 tiles of 14x14, two channel chunks (64 + 56), Cin not a multiple of 32
+    (1, 14, 80, 200, 1),        # single tile, 4 chunks (64,64,64,8), 3 k-blocks
+    (3, 56, 24, 72, 2),         # stride 2: 56 -> 28 = 4x4 tiles of 7x7
+    (2, 7, 160, 960, 1),        # 7x7: tile larger than the image, 15 chunks
+    (1, 112, 16, 64, 2),        # the big one: 112 -> 56, 8x8 tiles, single chunk / k-block
+])
+def test_xdw_fused_kernel(native_lib, B, H, Cin, mid, stride):
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, Cin, H, H, generator=g)
+    w1 = torch.randn(mid, Cin, 1, 1, generator=g) / Cin ** 0.5
+    s1, b1 = torch.rand(mid, generator=g) + 0.5, torch.randn(mid, generator=g) * 0.2
+    wd = torch.randn(mid, 1, 3, 3, generator=g) / 3.0
+    s2, b2 = torch.rand(mid, generator=g) + 0.5, torch.randn(mid, generator=g) * 0.2
+    dd = torch.float64
+    e = F.relu(F.conv2d(x.to(dd), w1.to(dd)) * s1.to(dd).view(1, -1, 1, 1) + b1.to(dd).view(1, -1, 1, 1))
+    ref = F.relu(tf_same_dw(e, wd.to(dd), stride) * s2.to(dd).view(1, -1, 1, 1) + b2.to(dd).view(1, -1, 1, 1)).float()
+    Ho = (H + stride - 1) // stride
+    xd, w1d = nhwc(x).to(DEV), w1.view(mid, Cin).contiguous().to(DEV)
+    wdd = wd.view(mid, 9).t().contiguous().to(DEV)                      # [9][mid]
+    s1d, b1d, s2d, b2d = s1.to(DEV), b1.to(DEV), s2.to(DEV), b2.to(DEV)
+    out = torch.full((B, Ho, Ho, mid), float("nan"), device=DEV)
+    rc = native_lib.smk_debug_xdw(P(xd), B, H, H, Cin, P(w1d), P(s1d), P(b1d), mid, P(wdd), P(s2d), P(b2d), stride, 0, P(out), stream())
+    assert rc == 0, native_lib.smk_last_error()
+    torch.cuda.synchronize()
+    got = out.permute(0, 3, 1, 2).cpu()
+    assert torch.isfinite(got).all(), "unwritten outputs: %d" % int((~torch.isfinite(got)).sum())
+    err = (got - ref).abs().max().item()
+    assert err <= 3e-3 * ref.abs().max().item(), "max err %.3g vs scale %.3g" % (err, ref.abs().max().item())
+
+
+def test_xdw_fused_exact_on_small_integers(native_lib):
+    g = torch.Generator().manual_seed(32)
+    for stride, H in ((1, 28), (2, 28)):
+        B, Cin, mid = 2, 24, 72
+        x = torch.randint(-2, 3, (B, Cin, H, H), generator=g).float()
+        w1 = torch.randint(-1, 2, (mid, Cin, 1, 1), generator=g).float()
+        wd = torch.randint(-1, 2, (mid, 1, 3, 3), generator=g).float()
+        one, zero = torch.ones(mid), torch.zeros(mid)
+        ref = F.relu(tf_same_dw(F.relu(F.conv2d(x, w1)), wd, stride))
+        Ho = (H + stride - 1) // stride
+        xd, w1d, wdd = nhwc(x).to(DEV), w1.view(mid, Cin).contiguous().to(DEV), wd.view(mid, 9).t().contiguous().to(DEV)
+        od, zd = one.to(DEV), zero.to(DEV)
+        out = torch.full((B, Ho, Ho, mid), float("nan"), device=DEV)
+        rc = native_lib.smk_debug_xdw(P(xd), B, H, H, Cin, P(w1d), P(od), P(zd), mid, P(wdd), P(od), P(zd), stride, 0, P(out), stream())
+        assert rc == 0, native_lib.smk_last_error()
+        torch.cuda.synchronize()
+        assert torch.equal(out.permute(0, 3, 1, 2).cpu(), ref), "stride %d" % stride

@@ -293,3 +293,21 @@ def test_encoder_tf32_tensor_core_path(encoder):
         assert float((o[k].cpu() - ref[k]).abs().max()) <= 5e-3 * scale, k
     o32 = encoder(img.to(DEV))
     assert float((o["shape_params"] - o32["shape_params"]).abs().max()) > 0      # really a different arithmetic path
+
+
+def test_encoder_fused_blocks_path(encoder):
+    """precision = 2: inverted-residual blocks run expand+depthwise as one tcgen05 kernel."""
+    import copy
+    from oracle import encoder_ref
+    ef = copy.deepcopy(encoder)
+    ef.precision = 2
+    img = synth_inputs.images(5, 402)
+    ref = encoder_ref.encoder_forward_ref({k: v.cpu() for k, v in encoder.state_dict().items()}, img)
+    o = ef(img.to(DEV))
+    for k in o:
+        scale = max(float(ref[k].abs().max()), 1.0)
+        assert float((o[k].cpu() - ref[k]).abs().max()) <= 5e-3 * scale, k
+    a = ef(synth_inputs.images(32, 403).to(DEV))
+    b = ef(synth_inputs.images(32, 403)[7:9].contiguous().to(DEV))
+    for k in a:
+        rel_close(b[k], a[k][7:9], 1e-5, 1e-6)
