@@ -180,7 +180,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16, help="faces per CPU-baseline pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel breakdown JSON here")
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "tf32-unfused"],
                     help="tf32: 1x1/3x3/transposed convs on tcgen05 tensor cores (the reference's own cuDNN default); "
                          "fp32: every conv on the exact fp32 CUDA-core path")
     args = ap.parse_args()
@@ -220,13 +220,14 @@ def main():
     enc = smirk_b200.SmirkEncoder()
     enc.load_state_dict(synth_inputs.random_state_dict(enc.state_dict(), seed=7))
     enc = enc.eval().to(dev)
-    enc.precision = 1 if args.precision == "tf32" else 0
+    # tf32 = tensor-core convs + fused expand/depthwise blocks in the encoder; tf32-unfused keeps one kernel per layer
+    enc.precision = {"fp32": 0, "tf32-unfused": 1, "tf32": 2}[args.precision]
     gen = None
     if args.generator:
         gen = smirk_b200.SmirkGenerator(6, 3, 32, 5)
         gen.load_state_dict(synth_inputs.random_state_dict(gen.state_dict(), seed=7))
         gen = gen.eval().to(dev)
-        gen.precision = enc.precision
+        gen.precision = min(enc.precision, 1)
     pipe = SmirkPipeline(enc, smirk_b200.FLAME().to(dev), smirk_b200.Renderer().to(dev), gen, device=dev)
 
     # rotating input set larger than L2 (126 MB): R batches of B x 602 KB
@@ -316,8 +317,8 @@ def main():
         # (profiles/*ncu_dram_traffic*.json: dram__bytes_read.sum + dram__bytes_write.sum); null if the
         # capture does not cover this configuration.
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_ncu_dram_traffic_c2_b32.json")
-        if os.path.exists(tpath) and B == 32 and gen is None and args.precision == "tf32":
+        tpath = os.path.join(ROOT, "profiles", "r01_ncu_dram_traffic_c2_b32_%s.json" % args.precision)
+        if os.path.exists(tpath) and B == 32 and gen is None:
             tk = json.load(open(tpath)).get("kernels", {}).get(top_tag.split(":")[0])
             if tk:
                 traffic = tk["traffic_bytes_per_launch"]
@@ -344,7 +345,7 @@ def main():
         line = {
             "metric": METRIC, "value": faces / (ms_total / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 convs (fp32 accumulate), f32 elsewhere" if args.precision == "tf32" else "f32", "data": "synthetic",
+            "dtype": "tf32 convs (fp32 accumulate), f32 elsewhere" if args.precision != "fp32" else "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "precision": args.precision, "global_batch": B * world, "faces_per_gpu_per_step": B,
                        "image": "224x224 RGB fp32", "parallelism": "frame-shard dp%d" % world,
                        "l2_policy": "inputs rotate over %d batches (%.0f MB > 126 MB L2)" % (R, R * per / 1e6),

@@ -6,13 +6,14 @@
 // Here it only ever exists in TMEM and shared memory:
 //
 //   CTA = one 16x16-pixel window of e for one image (a 14x14 tile of outputs + halo for stride 1, a 7x7
-//         tile for stride 2), looping over the expanded channels in chunks of 64.
+//         tile for stride 2) x one group of 32-channel chunks of the expanded tensor (the depthwise conv
+//         makes channel chunks independent, so low-resolution layers still fill the GPU); 2 CTAs per SM.
 //   warp 0      TMA producer: two 16x8-pixel boxes of x (4-D tiled tensor map over NHWC, halo pixels
-//               outside the image zero-filled by the hardware) + a 64-row box of the 1x1 weights per k-block.
-//   warp 1      tcgen05.mma kind::tf32, M = 2 x 128 window pixels, N = 64 channels, accumulators
-//               double-buffered in TMEM (4 x 64 columns) so chunk c+1 is multiplied while chunk c drains.
+//               outside the image zero-filled by the hardware) + a 32-row box of the 1x1 weights per k-block.
+//   warp 1      tcgen05.mma kind::tf32, M = 2 x 128 window pixels, N = 32 channels, accumulators
+//               double-buffered in TMEM (4 x 32 columns) so chunk c+1 is multiplied while chunk c drains.
 //   warps 2-9   (a) TMEM -> BN1 + ReLU (+ zero outside the image, which is what the depthwise conv's zero
-//               padding of e means) -> shared-memory window E[256][64];
+//               padding of e means) -> shared-memory window E[256][32];
 //               (b) depthwise 3x3 over E on the CUDA cores (float4 over channels), BN2 + ReLU, optional
 //               TF32 rounding, coalesced 256-byte stores of d.
 //
@@ -27,15 +28,15 @@ namespace {
 constexpr int BKB = 128, BK = 32, UMMA_K = 8;
 constexpr int WIN = 16;                         // window edge (pixels of e)
 constexpr int HALF_BYTES = 128 * BKB;           // one 16x8-pixel box, 32 channels: 16 KiB
-constexpr int NC = 64;                          // expanded channels per chunk
-constexpr int B_BYTES = NC * BKB;               // 8 KiB
-constexpr int STAGE_BYTES = 2 * HALF_BYTES + B_BYTES;   // 40 KiB
-constexpr int STAGES = 3;
-constexpr int E_PITCH = NC + 4;                 // floats; 272-byte rows: conflict-free 16-byte column writes
-constexpr int E_BYTES = 256 * E_PITCH * 4;      // 69 632 B
+constexpr int NC = 32;                          // expanded channels per chunk
+constexpr int B_BYTES = NC * BKB;               // 4 KiB
+constexpr int STAGE_BYTES = 2 * HALF_BYTES + B_BYTES;   // 36 KiB
+constexpr int STAGES = 2;
+constexpr int E_PITCH = NC + 4;                 // floats; 144-byte rows (odd multiple of 16 B): conflict-free 16-byte column writes
+constexpr int E_BYTES = 256 * E_PITCH * 4;      // 36 864 B
 constexpr int NUM_WORKERS = 256;
 constexpr int NUM_THREADS = 64 + NUM_WORKERS;
-constexpr uint32_t TMEM_COLS = 256;             // (2 buffers) x (2 halves) x 64 columns
+constexpr uint32_t TMEM_COLS = 128;             // (2 buffers) x (2 halves) x 32 columns
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -110,7 +111,9 @@ __device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, 256
 
 struct XdwArgs {
     int H, W, Ho, Wo;              // e (= x) resolution and output resolution
-    int mid, nkb, nchunks;         // expanded channels, 32-wide k-blocks of Cin, 64-wide channel chunks
+    int mid, nkb, nchunks;         // expanded channels, 32-wide k-blocks of Cin, 32-wide channel chunks
+    int groups, chunks_per_group;  // a group owns chunks [g*cpg, min((g+1)*cpg, nchunks)); item = ((img*tiles_y + ty)*tiles_x + tx)*groups + g
+    int n_items;
     int pad;                       // TF-SAME pad_begin of the depthwise conv (1 for stride 1, 0 for stride 2 on even sizes)
     int tiles_x, tiles_y;          // output tiles per image
     const float* scale1; const float* bias1;        // folded BN of the 1x1 conv        [mid]
@@ -121,7 +124,7 @@ struct XdwArgs {
 };
 
 template <int STRIDE>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const XdwArgs a) {
     constexpr int TO = STRIDE == 1 ? 14 : 7;                    // output tile edge
     constexpr uint32_t IDESC = make_idesc(128, NC);
@@ -135,9 +138,20 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int img = blockIdx.z;
-    const int oh0 = blockIdx.y * TO, ow0 = blockIdx.x * TO;
-    const int ey0 = oh0 * STRIDE - a.pad, ex0 = ow0 * STRIDE - a.pad;     // window origin in e / x coordinates
+    // Persistent CTA: work item = (image, output tile, channel-chunk group), items strided over the grid.
+    // All three roles walk the same item sequence; the smem ring and the TMEM double buffer run across
+    // item boundaries, so the x window / weights of item i+1 are in flight (and multiplied) while the
+    // workers are still busy with item i.
+    struct Item { int img, oh0, ow0, c_begin, c_end; };
+    auto decode = [&](int item) {
+        Item w;
+        const int grp = item % a.groups; int r = item / a.groups;
+        const int tx = r % a.tiles_x; r /= a.tiles_x;
+        const int ty = r % a.tiles_y; w.img = r / a.tiles_y;
+        w.oh0 = ty * TO; w.ow0 = tx * TO;
+        w.c_begin = grp * a.chunks_per_group; w.c_end = min(a.nchunks, w.c_begin + a.chunks_per_group);
+        return w;
+    };
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
@@ -159,24 +173,30 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         if (lane == 0) {
             // ===== TMA producer: (x window, W1 chunk) per k-block, for every channel chunk =====
             int it = 0;
-            for (int c = 0; c < a.nchunks; ++c)
-                for (int kb = 0; kb < a.nkb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&empty[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
-                    uint8_t* st = smem + s * STAGE_BYTES;
-                    mbar_expect_tx(&full[s], (uint32_t)STAGE_BYTES);
-                    tma_load_4d(&tmX, st, &full[s], kb * BK, ex0, ey0, img);
-                    tma_load_4d(&tmX, st + HALF_BYTES, &full[s], kb * BK, ex0, ey0 + 8, img);
-                    tma_load_2d(&tmW, st + 2 * HALF_BYTES, &full[s], kb * BK, c * NC);
-                }
+            for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+                const Item w = decode(item);
+                const int ey0 = w.oh0 * STRIDE - a.pad, ex0 = w.ow0 * STRIDE - a.pad;     // window origin in e / x coordinates
+                for (int c = w.c_begin; c < w.c_end; ++c)
+                    for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        mbar_wait(&empty[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+                        uint8_t* st = smem + s * STAGE_BYTES;
+                        mbar_expect_tx(&full[s], (uint32_t)STAGE_BYTES);
+                        tma_load_4d(&tmX, st, &full[s], kb * BK, ex0, ey0, w.img);
+                        tma_load_4d(&tmX, st + HALF_BYTES, &full[s], kb * BK, ex0, ey0 + 8, w.img);
+                        tma_load_2d(&tmW, st + 2 * HALF_BYTES, &full[s], kb * BK, c * NC);
+                    }
+            }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer =====
-            int it = 0;
-            for (int c = 0; c < a.nchunks; ++c) {
-                const int buf = c & 1;
-                mbar_wait(&acc_empty[buf], ((uint32_t)(c >> 1) & 1u) ^ 1u);
+            int it = 0, cc = 0;                             // ring iteration / accumulator-buffer use counters
+            for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+              const Item w = decode(item);
+              for (int c = w.c_begin; c < w.c_end; ++c, ++cc) {
+                const int buf = cc & 1;
+                mbar_wait(&acc_empty[buf], ((uint32_t)(cc >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
                 for (int kb = 0; kb < a.nkb; ++kb, ++it) {
                     const int s = it % STAGES;
@@ -193,37 +213,41 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                     tcgen05_commit(&empty[s]);
                 }
                 tcgen05_commit(&acc_full[buf]);
+              }
             }
         }
     } else {
         // ===== workers: 8 warps =====
         const int wid = warp - 2;                          // 0..7
         const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
-        const int colh = wid >> 2;                         // which 32 of the chunk's 64 columns (warps {2..5} vs {6..9} cover all quarters)
+        const int half = wid >> 2;                         // warps {2..5} drain the upper 16x8 pixels, {6..9} the lower
         const int t = threadIdx.x - 64;                    // 0..255
-        const int cq = t & 15, slot = t >> 4;              // depthwise role: channel quad within the chunk, output slot
-        for (int c = 0; c < a.nchunks; ++c) {
-            const int buf = c & 1;
+        const int cq = t & 7, slot = t >> 3;               // depthwise role: channel quad within the chunk, output slot (0..31)
+        int cc = 0;
+        for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+          const Item w = decode(item);
+          const int img = w.img, oh0 = w.oh0, ow0 = w.ow0;
+          const int ey0 = oh0 * STRIDE - a.pad, ex0 = ow0 * STRIDE - a.pad;
+          for (int c = w.c_begin; c < w.c_end; ++c, ++cc) {
+            const int buf = cc & 1;
             const int ch0 = c * NC;
             const int nvalid = min(NC, a.mid - ch0);       // channels of this chunk that exist
-            mbar_wait(&acc_full[buf], (uint32_t)(c >> 1) & 1u);
+            mbar_wait(&acc_full[buf], (uint32_t)(cc >> 1) & 1u);
             tcgen05_fence_after();
             // (a) TMEM -> BN1 + ReLU -> E   (rows = window pixels, lane = pixel)
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            {
                 float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * 2 + half) * NC + colh * 32), v);
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * 2 + half) * NC), v);
                 const int r = quarter * 32 + lane;                       // row within the half: r = hh*16 + ww
                 const int ey = ey0 + half * 8 + (r >> 4), ex = ex0 + (r & 15);
                 const bool inside = ey >= 0 && ey < a.H && ex >= 0 && ex < a.W;
-                float* erow = E + (size_t)(half * 128 + r) * E_PITCH + colh * 32;
+                float* erow = E + (size_t)(half * 128 + r) * E_PITCH;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const int ch = ch0 + colh * 32 + j;
                     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (inside && colh * 32 + j < nvalid) {
-                        const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale1 + ch));
-                        const float4 bi = __ldg(reinterpret_cast<const float4*>(a.bias1 + ch));
+                    if (inside && j < nvalid) {
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale1 + ch0 + j));
+                        const float4 bi = __ldg(reinterpret_cast<const float4*>(a.bias1 + ch0 + j));
                         o.x = fmaxf(fmaf(v[j], sc.x, bi.x), 0.f); o.y = fmaxf(fmaf(v[j + 1], sc.y, bi.y), 0.f);
                         o.z = fmaxf(fmaf(v[j + 2], sc.z, bi.z), 0.f); o.w = fmaxf(fmaf(v[j + 3], sc.w, bi.w), 0.f);
                     }
@@ -242,7 +266,7 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                 for (int q = 0; q < 9; ++q) k[q] = __ldg(reinterpret_cast<const float4*>(a.wdw + (size_t)q * a.mid + ch));
                 const float4 s2 = __ldg(reinterpret_cast<const float4*>(a.scale2 + ch));
                 const float4 b2 = __ldg(reinterpret_cast<const float4*>(a.bias2 + ch));
-                for (int p = slot; p < TO * TO; p += 16) {
+                for (int p = slot; p < TO * TO; p += 32) {
                     const int oy = p / TO, ox = p - oy * TO;
                     const int oh = oh0 + oy, ow = ow0 + ox;
                     if (oh >= a.Ho || ow >= a.Wo) continue;
@@ -265,6 +289,7 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                 }
             }
             worker_barrier();                              // E is free for the next chunk
+          }
         }
     }
     __syncthreads();
@@ -319,6 +344,12 @@ int xdw_conv(const XdwConv& p, cudaStream_t st) {
     }
     XdwArgs a{};
     a.H = p.H; a.W = p.W; a.Ho = Ho; a.Wo = Wo; a.mid = p.mid; a.nkb = cdiv(p.Cin, BK); a.nchunks = cdiv(p.mid, NC);
+    {   // split the channel chunks over enough CTAs to fill 148 SMs x 2 CTAs
+        const long tiles = (long)cdiv(Wo, TO) * cdiv(Ho, TO) * p.B;
+        int groups = (int)std::min<long>(a.nchunks, std::max<long>(1, (2 * 148 + tiles - 1) / tiles));
+        a.chunks_per_group = cdiv(a.nchunks, groups);
+        a.groups = cdiv(a.nchunks, a.chunks_per_group);
+    }
     a.pad = p.stride == 1 ? 1 : 0;
     a.tiles_x = cdiv(Wo, TO); a.tiles_y = cdiv(Ho, TO);
     a.scale1 = p.scale1; a.bias1 = p.bias1; a.wdw = p.wdw; a.scale2 = p.scale2; a.bias2 = p.bias2; a.out = p.out; a.round_out = p.round_out;
@@ -335,7 +366,8 @@ int xdw_conv(const XdwConv& p, cudaStream_t st) {
         if (g_prof_detail) tag = prof_shape_tag(tag, (long)px_out, p.Cin, p.mid);
         SMK_TAG(tag, 4.0 * (px_in * p.Cin + px_out * p.mid + (double)p.mid * (p.Cin + 13)), 2.0 * px_in * p.Cin * p.mid + 18.0 * px_out * p.mid, st);
     }
-    dim3 grid(a.tiles_x, a.tiles_y, p.B);
+    a.n_items = a.tiles_x * a.tiles_y * p.B * a.groups;
+    dim3 grid((unsigned)std::min(a.n_items, 2 * 148));          // persistent: 2 CTAs per SM
     if (p.stride == 1) xdw_kernel<1><<<grid, NUM_THREADS, smem, st>>>(tmX, tmW, a);
     else xdw_kernel<2><<<grid, NUM_THREADS, smem, st>>>(tmX, tmW, a);
     SMK_CHECK_LAUNCH();

@@ -20,7 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--generator", action="store_true")
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "tf32-unfused"])
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
@@ -35,13 +35,13 @@ def main():
     enc = smirk_b200.SmirkEncoder()
     enc.load_state_dict(synth_inputs.random_state_dict(enc.state_dict(), seed=7))
     enc = enc.eval().to(dev)
-    enc.precision = 1 if args.precision == "tf32" else 0
+    enc.precision = {"fp32": 0, "tf32-unfused": 1, "tf32": 2}[args.precision]
     gen = None
     if args.generator:
         gen = smirk_b200.SmirkGenerator(6, 3, 32, 5)
         gen.load_state_dict(synth_inputs.random_state_dict(gen.state_dict(), seed=7))
         gen = gen.eval().to(dev)
-        gen.precision = enc.precision
+        gen.precision = min(enc.precision, 1)
     pipe = SmirkPipeline(enc, smirk_b200.FLAME().to(dev), smirk_b200.Renderer().to(dev), gen, device=dev)
     B = args.batch
     imgs = [synth_inputs.images(B, 100 + i).to(dev) for i in range(4)]
