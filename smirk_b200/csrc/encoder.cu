@@ -210,6 +210,11 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
     // overlap; join before returning.  Event record/wait on other streams is legal under stream capture,
     // so a CUDA graph of the caller's stream gets three parallel branches.
     const bool concurrent = !smk::profiling();   // the event profiler wants one kernel at a time
+    {   // all three stems in one pass over the image (it is the only tensor the backbones share)
+        const float* sw[3]; const float* ss[3]; const float* sb[3]; float* so[3];
+        for (int i = 0; i < 3; ++i) { sw[i] = h->bb[i].stem.w; ss[i] = h->bb[i].stem.scale; sb[i] = h->bb[i].stem.bias; so[i] = bufs[i][0]; }
+        if (int rc = smk::stem_conv3(img, B, 224, 224, sw, ss, sb, so, main_st)) return rc;
+    }
     if (concurrent) {
         SMK_CHECK_CUDA(cudaEventRecord(h->fork, main_st));
         for (int s = 0; s < 2; ++s) SMK_CHECK_CUDA(cudaStreamWaitEvent(h->side[s], h->fork, 0));
@@ -219,8 +224,7 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
         cudaStream_t st = (i == 0 || !concurrent) ? main_st : h->side[i - 1];
         float* const* buf = bufs[i];
         float *x = buf[0], *y = buf[1], *e = buf[2], *d = buf[3];
-        int rc = smk::stem_conv(img, B, 224, 224, bb.stem.w, bb.stem.scale, bb.stem.bias, x, st);
-        if (rc) return rc;
+        int rc = 0;
         int res = 112;
         for (const Block& b : bb.blocks) {
             int ro = (res + b.stride - 1) / b.stride;

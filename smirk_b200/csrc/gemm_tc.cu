@@ -376,7 +376,16 @@ int tc_conv(const TcConv& p, cudaStream_t st) {
     SMK_REQUIRE(p.N % 4 == 0 && p.K % 4 == 0 && p.ld_in % 4 == 0 && p.ld_out % 4 == 0, "tc_conv: N, K, ld must be multiples of 4");
     SMK_REQUIRE(p.mode == 0 || (p.Cin % BK == 0 && p.K == 9 * p.Cin), "tc_conv: 3x3 mode needs Cin %% 32 == 0 (got %d)", p.Cin);
     SMK_REQUIRE(p.store != 1 || ((p.N / 4) % 32 == 0), "tc_conv: pixel-shuffle store needs Cout %% 32 == 0");
-    const int BN = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
+    int BN = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
+    // Few-tile, deep-K problems (the encoder's 7x7 / 14x14 projections: M = 1568..6272, K up to 960) are a serial
+    // chain of k-blocks on a handful of SMs: narrower N tiles put more CTAs to work and a deeper ring keeps
+    // more TMA loads in flight per CTA.
+    const int nkb_all = cdiv(p.K, BK);
+    bool deep_small = false;
+    if (nkb_all >= 6 && p.store != 1) {
+        while (BN > 32 && (long)cdiv(M, BM) * cdiv(p.N, BN) < 148) BN >>= 1;
+        deep_small = (long)cdiv(M, BM) * cdiv(p.N, BN) <= 2 * 148;
+    }
     CUtensorMap tmA, tmB;
     TcArgs a{};
     a.M = M; a.N = p.N; a.nkb = cdiv(p.K, BK); a.mode = p.mode == 0 ? 0 : 1; a.H = p.H; a.W = p.W;
@@ -402,6 +411,8 @@ int tc_conv(const TcConv& p, cudaStream_t st) {
     // Shallow-K layers (the encoder's 1x1 convs) are HBM-bound: a 2-stage ring keeps the footprint small so
     // 3-5 CTAs share an SM and hide each other's prologue/epilogue; deep-K layers get a deeper ring.
     const bool shallow = a.nkb <= 2;
+    if (deep_small && BN == 32) return launch<32, 8, 1>(tmA, tmB, a, st);
+    if (deep_small && BN == 64) return launch<64, 8, 1>(tmA, tmB, a, st);
     if (BN == 32) return shallow ? launch<32, 2, 5>(tmA, tmB, a, st) : launch<32, 4, 2>(tmA, tmB, a, st);
     if (BN == 64) return shallow ? launch<64, 2, 4>(tmA, tmB, a, st) : launch<64, 4, 2>(tmA, tmB, a, st);
     return shallow ? launch<128, 2, 3>(tmA, tmB, a, st) : launch<128, 3, 2>(tmA, tmB, a, st);

@@ -304,6 +304,50 @@ stem_conv_kernel(const float* __restrict__ img, int B, int H, int W, int Ho, int
     }
 }
 
+// The three backbones' stems read the same image: one pass over the pixels produces all 3 x 16 channels.
+struct Stem3 { const float* w[3]; const float* scale[3]; const float* bias[3]; float* out[3]; };
+
+__global__ void __launch_bounds__(128)
+stem_conv3_kernel(const float* __restrict__ img, int B, int H, int W, int Ho, int Wo, int pad, Stem3 p) {
+    __shared__ float sw[27 * 48];                  // [tap][group*16 + co]
+    __shared__ float ss[48], sb[48];
+    for (int i = threadIdx.x; i < 27 * 48; i += blockDim.x) { int tap = i / 48, gc = i % 48; sw[i] = p.w[gc / 16][tap * 16 + gc % 16]; }
+    if (threadIdx.x < 48) { ss[threadIdx.x] = p.scale[threadIdx.x / 16][threadIdx.x % 16]; sb[threadIdx.x] = p.bias[threadIdx.x / 16][threadIdx.x % 16]; }
+    __syncthreads();
+    long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (long)B * Ho * Wo) return;
+    int ow = (int)(pix % Wo); long t = pix / Wo; int oh = (int)(t % Ho); int b = (int)(t / Ho);
+    float acc[48];
+#pragma unroll
+    for (int i = 0; i < 48; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            int ih = oh * 2 + ky - pad;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                int iw = ow * 2 + kx - pad;
+                float x = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(img + (((size_t)b * 3 + c) * H + ih) * W + iw) : 0.f;
+                const float* wk = sw + ((c * 3 + ky) * 3 + kx) * 48;
+#pragma unroll
+                for (int i = 0; i < 48; ++i) acc[i] = fmaf(x, wk[i], acc[i]);
+            }
+        }
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        float4* o = reinterpret_cast<float4*>(p.out[g] + (size_t)pix * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = g * 16 + q * 4;
+            float4 v;
+            v.x = fmaxf(fmaf(acc[i + 0], ss[i + 0], sb[i + 0]), 0.f); v.y = fmaxf(fmaf(acc[i + 1], ss[i + 1], sb[i + 1]), 0.f);
+            v.z = fmaxf(fmaf(acc[i + 2], ss[i + 2], sb[i + 2]), 0.f); v.w = fmaxf(fmaf(acc[i + 3], ss[i + 3], sb[i + 3]), 0.f);
+            o[q] = v;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 maxpool2x2_kernel(const float* __restrict__ in, int ld_in, int B, int H, int W, int C, float* __restrict__ out) {
     const int Ho = H >> 1, Wo = W >> 1, C4 = C >> 2;
@@ -408,6 +452,17 @@ int stem_conv(const float* img, int B, int H, int W, const float* w, const float
     int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
     SMK_TAG("stem_conv", 4.0 * ((double)B * 3 * H * W + (double)B * Ho * Wo * 16 + 27 * 16 + 32), 2.0 * 27 * 16 * (double)B * Ho * Wo, st);
     stem_conv_kernel<<<cdiv((long)B * Ho * Wo, 128), 128, 0, st>>>(img, B, H, W, Ho, Wo, same_pad_begin(H, 2), w, scale, bias, out);
+    SMK_CHECK_LAUNCH();
+    return 0;
+}
+
+int stem_conv3(const float* img, int B, int H, int W, const float* const w[3], const float* const scale[3],
+               const float* const bias[3], float* const out[3], cudaStream_t st) {
+    int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    Stem3 p;
+    for (int g = 0; g < 3; ++g) { p.w[g] = w[g]; p.scale[g] = scale[g]; p.bias[g] = bias[g]; p.out[g] = out[g]; }
+    SMK_TAG("stem_conv3", 4.0 * ((double)B * 3 * H * W + (double)B * Ho * Wo * 48 + 27 * 48 + 96), 2.0 * 27 * 48 * (double)B * Ho * Wo, st);
+    stem_conv3_kernel<<<cdiv((long)B * Ho * Wo, 128), 128, 0, st>>>(img, B, H, W, Ho, Wo, same_pad_begin(H, 2), p);
     SMK_CHECK_LAUNCH();
     return 0;
 }

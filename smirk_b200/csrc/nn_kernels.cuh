@@ -35,6 +35,9 @@ int dwconv3x3(const float* in, int B, int H, int W, int C, int stride, const flo
 // Stem: NCHW fp32 image -> NHWC, 3x3 stride 2 TF-SAME, Cout = 16, fused scale/bias/ReLU.
 int stem_conv(const float* img_nchw, int B, int H, int W, const float* w /*[27][16]*/, const float* scale,
               const float* bias, float* out, cudaStream_t st);
+// Three 16-channel stems over the same image in one pass (the encoder's three backbones).
+int stem_conv3(const float* img_nchw, int B, int H, int W, const float* const w[3], const float* const scale[3],
+               const float* const bias[3], float* const out[3], cudaStream_t st);
 int maxpool2x2(const float* in, int ld_in, int B, int H, int W, int C, float* out, cudaStream_t st);
 int nchw_to_nhwc_pad(const float* in, int B, int C, int H, int W, int Cp, float* out, cudaStream_t st);
 // out[b, co, h, w] = sigmoid(bias[co] + sum_c in[b,h,w,c] * w[c][co])   (NHWC -> NCHW)
