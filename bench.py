@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--generator", action="store_true", help="include SmirkGenerator (configs[2], full cycle)")
     ap.add_argument("--cpu-sample", type=int, default=16, help="faces per CPU-baseline pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--slots", type=int, default=3, help="pipeline lanes: consecutive batches alternate over this many stream/graph replicas")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel breakdown JSON here")
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "tf32-unfused"],
                     help="tf32: 1x1/3x3/transposed convs on tcgen05 tensor cores (the reference's own cuDNN default); "
@@ -228,7 +229,7 @@ def main():
         gen.load_state_dict(synth_inputs.random_state_dict(gen.state_dict(), seed=7))
         gen = gen.eval().to(dev)
         gen.precision = min(enc.precision, 1)
-    pipe = SmirkPipeline(enc, smirk_b200.FLAME().to(dev), smirk_b200.Renderer().to(dev), gen, device=dev)
+    pipe = SmirkPipeline(enc, smirk_b200.FLAME().to(dev), smirk_b200.Renderer().to(dev), gen, device=dev, slots=args.slots)
 
     # rotating input set larger than L2 (126 MB): R batches of B x 602 KB
     per = B * 3 * 224 * 224 * 4 * (2 if gen is not None else 1)
@@ -238,13 +239,17 @@ def main():
     dev_imgs = [h.to(dev) for h in host_imgs]
     dev_masks = [h.to(dev) for h in host_masks] if gen is not None else None
     rec = pipe.capture(B)
+    for lane in range(1, pipe.slots):
+        pipe.capture(B, lane)
 
     def dev_step(i):
-        pipe.replay(dev_imgs[i % R], dev_masks[i % R] if gen is not None else None)
+        # batch i goes to lane i % slots (own stream + graph replica): consecutive batches overlap
+        pipe.submit(i, dev_imgs[i % R], dev_masks[i % R] if gen is not None else None)
 
     # ---- device-resident throughput (value) ----
     for i in range(W):
         dev_step(i)
+    pipe.join()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -255,6 +260,7 @@ def main():
     e0.record()
     for i in range(K):
         dev_step(W + i)
+    pipe.join()                                  # the timing stream waits for every lane
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -267,23 +273,23 @@ def main():
     # ---- end to end through the public host API (e2e) ----
     keys = ("rendered_img", "vertices", "params") + (("reconstructed_img",) if gen is not None else ())
     h2d, d2h = pipe.bytes_per_step(B, keys)
-    sets = pipe.host_buffers(B, keys)
     for i in range(W):
-        pipe.run_host(host_imgs[i % R], i & 1, host_masks[i % R] if gen is not None else None, keys)
+        pipe.run_host(host_imgs[i % R], i, host_masks[i % R] if gen is not None else None, keys)
+    pipe.join()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
+    last = None
     for i in range(K):
-        pipe.run_host(host_imgs[(W + i) % R], i & 1, host_masks[(W + i) % R] if gen is not None else None, keys)
-    for s in sets:
-        torch.cuda.current_stream(dev).wait_event(s["done"])
+        last = pipe.run_host(host_imgs[(W + i) % R], W + i, host_masks[(W + i) % R] if gen is not None else None, keys)
+    pipe.join()                                  # includes the copy streams: every D2H has landed
     e3.record()
     barrier()
     t2 = torch.tensor([e2.elapsed_time(e3)], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     ms_e2e = float(t2.item())
-    checksum = float(sets[(K - 1) & 1]["out"]["params"].double().abs().sum())   # touch the host result
+    checksum = float(last["params"].double().abs().sum())                       # touch the host result
 
     # ---- per-kernel breakdown (eager, event-bracketed launches; rank 0) ----
     breakdown, roof = None, None
@@ -349,9 +355,9 @@ def main():
             "config": {"workload": workload_name(args), "precision": args.precision, "global_batch": B * world, "faces_per_gpu_per_step": B,
                        "image": "224x224 RGB fp32", "parallelism": "frame-shard dp%d" % world,
                        "l2_policy": "inputs rotate over %d batches (%.0f MB > 126 MB L2)" % (R, R * per / 1e6),
-                       "execution": "CUDA graph replay, %d kernels per step" % rec["launches"]},
+                       "execution": "CUDA graph replay, %d kernels per step, %d-lane software pipeline over consecutive steps" % (rec["launches"], pipe.slots)},
             "e2e": {"value": faces / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / K, "api": "SmirkPipeline.run_host (pinned host in/out, 2-deep copy/compute overlap)",
+                    "ms_per_step": ms_e2e / K, "api": "SmirkPipeline.run_host (pinned host in/out, %d lanes, copies on a second stream)" % pipe.slots,
                     "host_checksum": checksum},
             "gpu_launches": int(rec["launches"]) * K,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,

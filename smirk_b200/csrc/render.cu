@@ -184,9 +184,28 @@ raster_tile_kernel(RenderDev d, const float* __restrict__ recs, const uint32_t* 
                 reinterpret_cast<const float4*>(rb + (size_t)s_cand[c0 + t] * REC)[q];
         }
         __syncthreads();
-        for (int t = 0; t < n; ++t) {
+        // A warp is one pixel row of the tile (same yf in every lane): lane l first tests candidates l and
+        // l+32 against the row's y and the row's x-extent, the ballots become the warp's work list, and
+        // only the survivors (about a third) reach the per-pixel tests.
+        const float xf_hi = pix_to_ndc(d.S - 1 - (int)(tx * TILE_W), d.S);                 // lane 0 sees the largest xf
+        const float xf_lo = pix_to_ndc(d.S - 1 - (int)(tx * TILE_W + TILE_W - 1), d.S);
+        const int lane = tid & 31;
+        unsigned long long live = 0ull;
+#pragma unroll
+        for (int hseg = 0; hseg < CHUNK / 32; ++hseg) {
+            const int t = hseg * 32 + lane;
+            bool ok = false;
+            if (t < n) {
+                const float4 bb = *reinterpret_cast<const float4*>(s_tri + t * REC + 16);    // xmin, xmax, ymin, ymax
+                ok = !(yf > bb.w || yf < bb.z) && !(xf_lo > bb.y || xf_hi < bb.x);
+            }
+            live |= (unsigned long long)__ballot_sync(0xffffffffu, ok) << (32 * hseg);
+        }
+        while (live) {
+            const int t = __ffsll((long long)live) - 1;
+            live &= live - 1;
             const float* r = s_tri + t * REC;
-            if (xf > r[17] || xf < r[16] || yf > r[19] || yf < r[18]) continue;       // outside bbox
+            if (xf > r[17] || xf < r[16]) continue;                                  // outside bbox in x (y was tested per row)
             float e0 = __fsub_rn(__fmul_rn(__fsub_rn(xf, r[2]), r[6]), __fmul_rn(__fsub_rn(yf, r[3]), r[7]));    // edge(p; v1, v2)
             float e1 = __fsub_rn(__fmul_rn(__fsub_rn(xf, r[4]), r[8]), __fmul_rn(__fsub_rn(yf, r[5]), r[9]));    // edge(p; v2, v0)
             float e2 = __fsub_rn(__fmul_rn(__fsub_rn(xf, r[0]), r[10]), __fmul_rn(__fsub_rn(yf, r[1]), r[11]));  // edge(p; v0, v1)

@@ -232,6 +232,15 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             const int buf = cc & 1;
             const int ch0 = c * NC;
             const int nvalid = min(NC, a.mid - ch0);       // channels of this chunk that exist
+            // this thread's depthwise weights / BN2 parameters: issued before waiting for the accumulator so
+            // their L2 latency hides behind the TMA -> MMA chain of the chunk
+            const bool dw_active = cq * 4 < nvalid;
+            const int chd = ch0 + (dw_active ? cq * 4 : 0);
+            float4 k[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) k[q] = __ldg(reinterpret_cast<const float4*>(a.wdw + (size_t)q * a.mid + chd));
+            const float4 s2 = __ldg(reinterpret_cast<const float4*>(a.scale2 + chd));
+            const float4 b2 = __ldg(reinterpret_cast<const float4*>(a.bias2 + chd));
             mbar_wait(&acc_full[buf], (uint32_t)(cc >> 1) & 1u);
             tcgen05_fence_after();
             // (a) TMEM -> BN1 + ReLU -> E   (rows = window pixels, lane = pixel)
@@ -259,13 +268,8 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             if (lane == 0) mbar_arrive(&acc_empty[buf]);   // this warp has drained its part of the accumulator
             worker_barrier();
             // (b) depthwise 3x3 over E: thread = (channel quad, output slot), outputs slot, slot+16, ...
-            if (cq * 4 < nvalid) {
-                const int ch = ch0 + cq * 4;
-                float4 k[9];
-#pragma unroll
-                for (int q = 0; q < 9; ++q) k[q] = __ldg(reinterpret_cast<const float4*>(a.wdw + (size_t)q * a.mid + ch));
-                const float4 s2 = __ldg(reinterpret_cast<const float4*>(a.scale2 + ch));
-                const float4 b2 = __ldg(reinterpret_cast<const float4*>(a.bias2 + ch));
+            if (dw_active) {
+                const int ch = chd;
                 for (int p = slot; p < TO * TO; p += 32) {
                     const int oy = p / TO, ox = p - oy * TO;
                     const int oh = oh0 + oy, ow = ow0 + ox;

@@ -5,13 +5,19 @@ This is the public entry point ``bench.py`` and the demos use for batched work:
 * ``forward(img)``            device tensors in, dict of device tensors out (what demo.py:107-112 does
                               with three module calls);
 * ``capture(B)`` / ``replay`` the same work recorded once into a CUDA graph (one launch per batch instead
-                              of ~250 kernel launches — the launch-bound regime of small batches);
-* ``run_host(img_pinned)``    end-to-end from pinned host memory: H2D copy, graph replay, D2H of the
-                              results into pinned buffers, double-buffered over two streams so the
-                              copies of batch i+1 overlap the kernels of batch i;
-* ``shard`` / ``all_gather``  frame-shard data parallelism (one process per GPU, contiguous split of the
-                              batch; a single NCCL all-gather of the final outputs — SURVEY.md §8e).
+                              of ~100 kernel launches — the launch-bound regime of small batches);
+* ``submit(i, img)`` / ``join`` software pipelining over ``slots`` lanes: each lane owns a replica of the
+                              modules (same weights, its own native handles, workspaces, graph and stream),
+                              so the serial FLAME -> rasteriser tail of batch i overlaps the encoder of
+                              batch i+1;
+* ``run_host(img_pinned, i)`` end-to-end from pinned host memory: H2D copy, graph replay, D2H of the
+                              results into pinned buffers; lane i % slots, copies on a second stream, so
+                              the copies of one batch overlap the kernels of the other;
+* ``shard_bounds`` / ``all_gather_frames``  frame-shard data parallelism (one process per GPU, contiguous
+                              split of the batch; a single NCCL all-gather of the final outputs — SURVEY.md §8e).
 """
+import copy
+
 import torch
 
 from . import _lib
@@ -45,22 +51,46 @@ def all_gather_frames(t, n_frames=None, group=None):
     return torch.cat([out[r * mx:r * mx + c] for r, c in enumerate(counts)], 0)
 
 
+class _Lane:
+    """One pipeline lane: a set of modules, a compute stream, a copy stream, per-batch-size graphs."""
+
+    def __init__(self, modules, device, own_stream):
+        self.encoder, self.flame, self.renderer, self.generator = modules
+        self.stream = torch.cuda.Stream(device=device) if own_stream else None
+        self.copy_stream = None
+        self.graphs = {}
+        self.host = {}
+        self.computed = torch.cuda.Event()
+        self.done = torch.cuda.Event()
+        self.staged = torch.cuda.Event()
+
+
 class SmirkPipeline:
     OUT_KEYS = ("rendered_img", "vertices", "transformed_vertices", "landmarks_fan", "landmarks_mp", "params")
 
-    def __init__(self, encoder, flame, renderer, generator=None, device="cuda:0"):
+    def __init__(self, encoder, flame, renderer, generator=None, device="cuda:0", slots=2):
         self.device = torch.device(device)
         self.encoder, self.flame, self.renderer, self.generator = encoder, flame, renderer, generator
-        self._graphs = {}
-        self._host = {}
+        self.slots = max(1, int(slots))
+        self._lanes = [_Lane((encoder, flame, renderer, generator), self.device, own_stream=False)]
+
+    def _lane(self, i):
+        """Lane 0 runs the caller's modules on the caller's stream; lanes >= 1 are replicas (deep copies:
+        same parameter values, separate native handles / workspaces) on their own streams."""
+        while len(self._lanes) <= i:
+            mods = tuple(copy.deepcopy(m) if m is not None else None
+                         for m in (self.encoder, self.flame, self.renderer, self.generator))
+            self._lanes.append(_Lane(mods, self.device, own_stream=True))
+        return self._lanes[i]
 
     # ---- plain forward (device in, device out) -----------------------------------------------------
     @torch.no_grad()
-    def forward(self, img, masked_img=None):
-        p = self.encoder(img)
-        fo = self.flame.forward(p)
-        ro = self.renderer.forward(fo["vertices"], p["cam"], landmarks_fan=fo["landmarks_fan"],
-                                   landmarks_mp=fo["landmarks_mp"])
+    def forward(self, img, masked_img=None, lane=0):
+        L = self._lane(lane)
+        p = L.encoder(img)
+        fo = L.flame.forward(p)
+        ro = L.renderer.forward(fo["vertices"], p["cam"], landmarks_fan=fo["landmarks_fan"],
+                                landmarks_mp=fo["landmarks_mp"])
         out = {
             "rendered_img": ro["rendered_img"], "vertices": fo["vertices"],
             "transformed_vertices": ro["transformed_vertices"], "landmarks_fan": ro["landmarks_fan"],
@@ -68,17 +98,18 @@ class SmirkPipeline:
             "params": torch.cat([p["pose_params"], p["cam"], p["shape_params"], p["expression_params"],
                                  p["eyelid_params"], p["jaw_params"]], 1),                      # [B,361]
         }
-        if self.generator is not None:
+        if L.generator is not None:
             if masked_img is None:
                 raise RuntimeError("SmirkPipeline: the generator stage needs `masked_img` (demo.py:165-167)")
-            out["reconstructed_img"] = self.generator(torch.cat([ro["rendered_img"], masked_img], 1))
+            out["reconstructed_img"] = L.generator(torch.cat([ro["rendered_img"], masked_img], 1))
         return out
 
     # ---- CUDA graph -----------------------------------------------------------------------------------
-    def capture(self, B):
+    def capture(self, B, lane=0):
         """Record forward() for batch size B into a CUDA graph with static input/output buffers."""
-        if B in self._graphs:
-            return self._graphs[B]
+        L = self._lane(lane)
+        if B in L.graphs:
+            return L.graphs[B]
         dev = self.device
         static_in = torch.zeros(B, 3, 224, 224, device=dev)
         static_mask = torch.zeros(B, 3, 224, 224, device=dev) if self.generator is not None else None
@@ -86,19 +117,20 @@ class SmirkPipeline:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                       # warm-up: builds handles, sizes workspaces
             for _ in range(2):
-                self.forward(static_in, static_mask)
+                self.forward(static_in, static_mask, lane)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
         n0 = _lib.lib().smk_launch_count()
         with torch.cuda.graph(g):
-            static_out = self.forward(static_in, static_mask)
+            static_out = self.forward(static_in, static_mask, lane)
         launches = _lib.lib().smk_launch_count() - n0
         rec = dict(graph=g, img=static_in, mask=static_mask, out=static_out, launches=int(launches))
-        self._graphs[B] = rec
+        L.graphs[B] = rec
         return rec
 
     def replay(self, img, masked_img=None):
+        """Lane 0, caller's stream: copy the inputs into the graph's static buffers and replay."""
         rec = self.capture(img.shape[0])
         rec["img"].copy_(img, non_blocking=True)
         if rec["mask"] is not None:
@@ -106,56 +138,83 @@ class SmirkPipeline:
         rec["graph"].replay()
         return rec["out"]
 
-    # ---- host-to-host (pinned) ------------------------------------------------------------------------
-    def host_buffers(self, B, keys=("rendered_img", "vertices", "params")):
-        """Two sets of pinned staging buffers (double buffering) for run_host()."""
-        key = (B, tuple(keys))
-        if key not in self._host:
-            rec = self.capture(B)
-            sets = []
-            for _ in range(2):
-                sets.append(dict(
-                    dev_in=torch.empty(B, 3, 224, 224, device=self.device),
-                    dev_mask=torch.empty(B, 3, 224, 224, device=self.device) if rec["mask"] is not None else None,
-                    dev_out={k: torch.empty_like(rec["out"][k]) for k in keys},
-                    out={k: torch.empty(rec["out"][k].shape, dtype=rec["out"][k].dtype).pin_memory() for k in keys},
-                    copy_stream=torch.cuda.Stream(device=self.device),
-                    done=torch.cuda.Event(), staged=torch.cuda.Event(), computed=torch.cuda.Event()))
-            self._host[key] = sets
-        return self._host[key]
+    # ---- software pipelining over lanes -------------------------------------------------------------
+    def submit(self, i, img, masked_img=None):
+        """Enqueue batch ``i`` on lane ``i % slots`` (its own stream; lane 0 = the caller's stream).  Inputs
+        must already be valid on the caller's current stream.  Outputs live in the lane's static buffers
+        until that lane is used again; call ``join()`` before reading them from the caller's stream."""
+        lane = i % self.slots
+        rec = self.capture(img.shape[0], lane)
+        L = self._lanes[lane]
+        cur = torch.cuda.current_stream(self.device)
+        if L.stream is None:
+            self.replay(img, masked_img)
+            return rec["out"]
+        L.stream.wait_stream(cur)                           # inputs ready
+        with torch.cuda.stream(L.stream):
+            rec["img"].copy_(img, non_blocking=True)
+            if rec["mask"] is not None:
+                rec["mask"].copy_(masked_img, non_blocking=True)
+            rec["graph"].replay()
+        return rec["out"]
 
-    def run_host(self, img_pinned, slot, masked_pinned=None, keys=("rendered_img", "vertices", "params")):
-        """One batch, host to host.  ``slot`` alternates 0/1 between consecutive calls so that the H2D
-        copy of this batch and the D2H copy of the previous one overlap compute.  Returns the pinned
-        output dict of this slot; call ``sets[slot]['done'].synchronize()`` before reading it."""
+    def join(self):
+        cur = torch.cuda.current_stream(self.device)
+        for L in self._lanes:
+            if L.stream is not None:
+                cur.wait_stream(L.stream)
+            if L.copy_stream is not None:
+                cur.wait_stream(L.copy_stream)
+
+    # ---- host-to-host (pinned) ------------------------------------------------------------------------
+    def host_buffers(self, B, lane, keys=("rendered_img", "vertices", "params")):
+        L = self._lane(lane)
+        key = (B, tuple(keys))
+        if key not in L.host:
+            rec = self.capture(B, lane)
+            L.host[key] = {k: torch.empty(rec["out"][k].shape, dtype=rec["out"][k].dtype).pin_memory() for k in keys}
+            if L.copy_stream is None:
+                L.copy_stream = torch.cuda.Stream(device=self.device)
+        return L.host[key]
+
+    def run_host(self, img_pinned, i, masked_pinned=None, keys=("rendered_img", "vertices", "params")):
+        """Batch ``i``, host to host, on lane ``i % slots``: H2D straight into the lane's static graph input
+        (copy stream), graph replay (lane stream), D2H of the results into the lane's pinned buffers (copy
+        stream).  A lane is strictly sequential; the other lane's copies and kernels overlap with it.
+        Returns the lane's pinned output dict — ``join()`` (or ``lane_done(i).synchronize()``) before reading."""
         B = img_pinned.shape[0]
-        s = self.host_buffers(B, keys)[slot]
-        rec = self.capture(B)
-        main = torch.cuda.current_stream(self.device)
-        cs = s["copy_stream"]
-        with torch.cuda.stream(cs):                         # H2D on the copy stream
-            cs.wait_event(s["done"])                        # previous use of this slot fully drained
-            s["dev_in"].copy_(img_pinned, non_blocking=True)
-            if s["dev_mask"] is not None:
-                s["dev_mask"].copy_(masked_pinned, non_blocking=True)
-            s["staged"].record(cs)
-        main.wait_event(s["staged"])
-        rec["img"].copy_(s["dev_in"], non_blocking=True)
-        if rec["mask"] is not None:
-            rec["mask"].copy_(s["dev_mask"], non_blocking=True)
-        rec["graph"].replay()
-        for k in keys:                                      # detach results from the graph's static buffers
-            s["dev_out"][k].copy_(rec["out"][k], non_blocking=True)
-        s["computed"].record(main)
-        with torch.cuda.stream(cs):                         # D2H on the copy stream
-            cs.wait_event(s["computed"])
+        lane = i % self.slots
+        out = self.host_buffers(B, lane, keys)
+        rec = self.capture(B, lane)
+        L = self._lanes[lane]
+        cur = torch.cuda.current_stream(self.device)
+        compute = L.stream if L.stream is not None else cur
+        cs = L.copy_stream
+        with torch.cuda.stream(cs):
+            cs.wait_event(L.done)                           # previous batch of this lane fully drained (D2H finished)
+            rec["img"].copy_(img_pinned, non_blocking=True)
+            if rec["mask"] is not None:
+                rec["mask"].copy_(masked_pinned, non_blocking=True)
+            L.staged.record(cs)
+        compute.wait_event(L.staged)
+        with torch.cuda.stream(compute):
+            rec["graph"].replay()
+            L.computed.record(compute)
+        with torch.cuda.stream(cs):
+            cs.wait_event(L.computed)
             for k in keys:
-                s["out"][k].copy_(s["dev_out"][k], non_blocking=True)
-            s["done"].record(cs)
-        return s["out"]
+                out[k].copy_(rec["out"][k], non_blocking=True)
+            L.done.record(cs)
+        return out
+
+    def lane_done(self, i):
+        return self._lanes[i % self.slots].done
 
     def bytes_per_step(self, B, keys=("rendered_img", "vertices", "params")):
         rec = self.capture(B)
         h2d = B * 3 * 224 * 224 * 4 * (2 if rec["mask"] is not None else 1)
         d2h = sum(rec["out"][k].numel() * rec["out"][k].element_size() for k in keys)
         return h2d, d2h
+
+    def launches_per_step(self, B):
+        return self.capture(B)["launches"]
