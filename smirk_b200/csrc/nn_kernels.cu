@@ -307,16 +307,32 @@ stem_conv_kernel(const float* __restrict__ img, int B, int H, int W, int Ho, int
 // The three backbones' stems read the same image: one pass over the pixels produces all 3 x 16 channels.
 struct Stem3 { const float* w[3]; const float* scale[3]; const float* bias[3]; float* out[3]; };
 
+// CTA = one output row (b, oh): the 3 channels x 3 input rows it needs are staged in shared memory with
+// coalesced 16-byte loads (the direct version issued 27 strided 4-byte loads per thread and was
+// latency-bound at 22 % occupancy); thread = output pixel, 48 accumulators.
+constexpr int STEM_MAXW = 512;                     // staged row length (floats), >= W + 2
 __global__ void __launch_bounds__(128)
 stem_conv3_kernel(const float* __restrict__ img, int B, int H, int W, int Ho, int Wo, int pad, Stem3 p) {
     __shared__ float sw[27 * 48];                  // [tap][group*16 + co]
     __shared__ float ss[48], sb[48];
+    __shared__ __align__(16) float sin_[9][STEM_MAXW];   // [c*3+ky][1 + iw]  (column 0 = left padding)
+    const int oh = blockIdx.x % Ho, b = blockIdx.x / Ho;
     for (int i = threadIdx.x; i < 27 * 48; i += blockDim.x) { int tap = i / 48, gc = i % 48; sw[i] = p.w[gc / 16][tap * 16 + gc % 16]; }
     if (threadIdx.x < 48) { ss[threadIdx.x] = p.scale[threadIdx.x / 16][threadIdx.x % 16]; sb[threadIdx.x] = p.bias[threadIdx.x / 16][threadIdx.x % 16]; }
+    {   // stage rows: element iw of row (c,ky) lands at sin_[c*3+ky][4 + iw] so 16-byte stores stay aligned; halo columns zeroed
+        const int W4 = W >> 2;
+        for (int i = threadIdx.x; i < 9 * W4; i += blockDim.x) {
+            const int r = i / W4, q = i - r * W4, c = r / 3, ky = r - c * 3;
+            const int ih = oh * 2 + ky - pad;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ih >= 0 && ih < H) v = __ldg(reinterpret_cast<const float4*>(img + (((size_t)b * 3 + c) * H + ih) * W) + q);
+            *reinterpret_cast<float4*>(&sin_[r][4 + 4 * q]) = v;
+        }
+        if (threadIdx.x < 9) { sin_[threadIdx.x][3] = 0.f; sin_[threadIdx.x][4 + W] = 0.f; sin_[threadIdx.x][5 + W] = 0.f; }
+    }
     __syncthreads();
-    long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= (long)B * Ho * Wo) return;
-    int ow = (int)(pix % Wo); long t = pix / Wo; int oh = (int)(t % Ho); int b = (int)(t / Ho);
+    for (int ow = threadIdx.x; ow < Wo; ow += blockDim.x) {
+    const long pix = ((long)b * Ho + oh) * Wo + ow;
     float acc[48];
 #pragma unroll
     for (int i = 0; i < 48; ++i) acc[i] = 0.f;
@@ -324,11 +340,9 @@ stem_conv3_kernel(const float* __restrict__ img, int B, int H, int W, int Ho, in
     for (int c = 0; c < 3; ++c)
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-            int ih = oh * 2 + ky - pad;
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                int iw = ow * 2 + kx - pad;
-                float x = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(img + (((size_t)b * 3 + c) * H + ih) * W + iw) : 0.f;
+                const float x = sin_[c * 3 + ky][4 + ow * 2 + kx - pad];
                 const float* wk = sw + ((c * 3 + ky) * 3 + kx) * 48;
 #pragma unroll
                 for (int i = 0; i < 48; ++i) acc[i] = fmaf(x, wk[i], acc[i]);
@@ -346,6 +360,7 @@ stem_conv3_kernel(const float* __restrict__ img, int B, int H, int W, int Ho, in
             o[q] = v;
         }
     }
+    }   // ow
 }
 
 __global__ void __launch_bounds__(256)
@@ -462,7 +477,8 @@ int stem_conv3(const float* img, int B, int H, int W, const float* const w[3], c
     Stem3 p;
     for (int g = 0; g < 3; ++g) { p.w[g] = w[g]; p.scale[g] = scale[g]; p.bias[g] = bias[g]; p.out[g] = out[g]; }
     SMK_TAG("stem_conv3", 4.0 * ((double)B * 3 * H * W + (double)B * Ho * Wo * 48 + 27 * 48 + 96), 2.0 * 27 * 48 * (double)B * Ho * Wo, st);
-    stem_conv3_kernel<<<cdiv((long)B * Ho * Wo, 128), 128, 0, st>>>(img, B, H, W, Ho, Wo, same_pad_begin(H, 2), p);
+    SMK_REQUIRE(W % 4 == 0 && W + 8 <= STEM_MAXW && same_pad_begin(H, 2) <= 1, "stem_conv3: unsupported image width %d", W);
+    stem_conv3_kernel<<<B * Ho, 128, 0, st>>>(img, B, H, W, Ho, Wo, same_pad_begin(H, 2), p);
     SMK_CHECK_LAUNCH();
     return 0;
 }

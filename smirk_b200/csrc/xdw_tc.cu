@@ -129,7 +129,9 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     constexpr int TO = STRIDE == 1 ? 14 : 7;                    // output tile edge
     constexpr uint32_t IDESC = make_idesc(128, NC);
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment for SWIZZLE_128B; offset arithmetic (not an integer round-trip of the pointer) keeps
+    // the shared address space visible to the compiler, so E is accessed with LDS/STS instead of generic LD/ST.
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* E = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + E_BYTES);
     uint64_t* empty = full + STAGES;
@@ -232,15 +234,8 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             const int buf = cc & 1;
             const int ch0 = c * NC;
             const int nvalid = min(NC, a.mid - ch0);       // channels of this chunk that exist
-            // this thread's depthwise weights / BN2 parameters: issued before waiting for the accumulator so
-            // their L2 latency hides behind the TMA -> MMA chain of the chunk
             const bool dw_active = cq * 4 < nvalid;
             const int chd = ch0 + (dw_active ? cq * 4 : 0);
-            float4 k[9];
-#pragma unroll
-            for (int q = 0; q < 9; ++q) k[q] = __ldg(reinterpret_cast<const float4*>(a.wdw + (size_t)q * a.mid + chd));
-            const float4 s2 = __ldg(reinterpret_cast<const float4*>(a.scale2 + chd));
-            const float4 b2 = __ldg(reinterpret_cast<const float4*>(a.bias2 + chd));
             mbar_wait(&acc_full[buf], (uint32_t)(cc >> 1) & 1u);
             tcgen05_fence_after();
             // (a) TMEM -> BN1 + ReLU -> E   (rows = window pixels, lane = pixel)
@@ -270,6 +265,11 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             // (b) depthwise 3x3 over E: thread = (channel quad, output slot), outputs slot, slot+16, ...
             if (dw_active) {
                 const int ch = chd;
+                float4 k[9];                                // (hoisting these above the accumulator wait costs spills: measured slower)
+#pragma unroll
+                for (int q = 0; q < 9; ++q) k[q] = __ldg(reinterpret_cast<const float4*>(a.wdw + (size_t)q * a.mid + ch));
+                const float4 s2 = __ldg(reinterpret_cast<const float4*>(a.scale2 + ch));
+                const float4 b2 = __ldg(reinterpret_cast<const float4*>(a.bias2 + ch));
                 for (int p = slot; p < TO * TO; p += 32) {
                     const int oy = p / TO, ox = p - oy * TO;
                     const int oh = oh0 + oy, ow = ow0 + ox;
