@@ -57,12 +57,12 @@ class _Lane:
     def __init__(self, modules, device, own_stream):
         self.encoder, self.flame, self.renderer, self.generator = modules
         self.stream = torch.cuda.Stream(device=device) if own_stream else None
-        self.copy_stream = None
         self.graphs = {}
         self.host = {}
         self.computed = torch.cuda.Event()
         self.done = torch.cuda.Event()
         self.staged = torch.cuda.Event()
+        self.consumed = torch.cuda.Event()
 
 
 class SmirkPipeline:
@@ -73,6 +73,7 @@ class SmirkPipeline:
         self.encoder, self.flame, self.renderer, self.generator = encoder, flame, renderer, generator
         self.slots = max(1, int(slots))
         self._lanes = [_Lane((encoder, flame, renderer, generator), self.device, own_stream=False)]
+        self._h2d = self._d2h = None
 
     def _lane(self, i):
         """Lane 0 runs the caller's modules on the caller's stream; lanes >= 1 are replicas (deep copies:
@@ -163,49 +164,66 @@ class SmirkPipeline:
         for L in self._lanes:
             if L.stream is not None:
                 cur.wait_stream(L.stream)
-            if L.copy_stream is not None:
-                cur.wait_stream(L.copy_stream)
+        for st in (getattr(self, "_h2d", None), getattr(self, "_d2h", None)):
+            if st is not None:
+                cur.wait_stream(st)
 
     # ---- host-to-host (pinned) ------------------------------------------------------------------------
     def host_buffers(self, B, lane, keys=("rendered_img", "vertices", "params")):
+        """Per-lane pinned output buffers + device staging buffers; one H2D and one D2H stream for the whole
+        pipeline (copies in one direction serialise on the link anyway)."""
         L = self._lane(lane)
         key = (B, tuple(keys))
         if key not in L.host:
             rec = self.capture(B, lane)
-            L.host[key] = {k: torch.empty(rec["out"][k].shape, dtype=rec["out"][k].dtype).pin_memory() for k in keys}
-            if L.copy_stream is None:
-                L.copy_stream = torch.cuda.Stream(device=self.device)
+            L.host[key] = dict(
+                out={k: torch.empty(rec["out"][k].shape, dtype=rec["out"][k].dtype).pin_memory() for k in keys},
+                dev_in=torch.empty_like(rec["img"]),
+                dev_mask=torch.empty_like(rec["mask"]) if rec["mask"] is not None else None,
+                dev_out={k: torch.empty_like(rec["out"][k]) for k in keys})
+            if getattr(self, "_h2d", None) is None:
+                self._h2d = torch.cuda.Stream(device=self.device)
+                self._d2h = torch.cuda.Stream(device=self.device)
         return L.host[key]
 
     def run_host(self, img_pinned, i, masked_pinned=None, keys=("rendered_img", "vertices", "params")):
-        """Batch ``i``, host to host, on lane ``i % slots``: H2D straight into the lane's static graph input
-        (copy stream), graph replay (lane stream), D2H of the results into the lane's pinned buffers (copy
-        stream).  A lane is strictly sequential; the other lane's copies and kernels overlap with it.
-        Returns the lane's pinned output dict — ``join()`` (or ``lane_done(i).synchronize()``) before reading."""
+        """Batch ``i``, host to host, three decoupled stages:
+          H2D stream   pinned images -> the lane's device staging buffer (as soon as that buffer is free);
+          lane stream  staging -> graph input, graph replay, graph outputs -> output staging;
+          D2H stream   output staging -> the lane's pinned result buffers.
+        With ``slots`` lanes the upload of batch i+1 and the download of batch i-1 overlap the kernels of
+        batch i.  Returns the lane's pinned output dict — ``join()`` (or ``lane_done(i).synchronize()``)
+        before reading it."""
         B = img_pinned.shape[0]
         lane = i % self.slots
-        out = self.host_buffers(B, lane, keys)
+        hb = self.host_buffers(B, lane, keys)
         rec = self.capture(B, lane)
         L = self._lanes[lane]
         cur = torch.cuda.current_stream(self.device)
         compute = L.stream if L.stream is not None else cur
-        cs = L.copy_stream
-        with torch.cuda.stream(cs):
-            cs.wait_event(L.done)                           # previous batch of this lane fully drained (D2H finished)
-            rec["img"].copy_(img_pinned, non_blocking=True)
-            if rec["mask"] is not None:
-                rec["mask"].copy_(masked_pinned, non_blocking=True)
-            L.staged.record(cs)
-        compute.wait_event(L.staged)
+        with torch.cuda.stream(self._h2d):
+            self._h2d.wait_event(L.consumed)                # staging input of this lane has been read by its previous batch
+            hb["dev_in"].copy_(img_pinned, non_blocking=True)
+            if hb["dev_mask"] is not None:
+                hb["dev_mask"].copy_(masked_pinned, non_blocking=True)
+            L.staged.record(self._h2d)
         with torch.cuda.stream(compute):
+            compute.wait_event(L.staged)
+            compute.wait_event(L.done)                      # output staging drained by the previous D2H of this lane
+            rec["img"].copy_(hb["dev_in"], non_blocking=True)
+            if rec["mask"] is not None:
+                rec["mask"].copy_(hb["dev_mask"], non_blocking=True)
+            L.consumed.record(compute)
             rec["graph"].replay()
-            L.computed.record(compute)
-        with torch.cuda.stream(cs):
-            cs.wait_event(L.computed)
             for k in keys:
-                out[k].copy_(rec["out"][k], non_blocking=True)
-            L.done.record(cs)
-        return out
+                hb["dev_out"][k].copy_(rec["out"][k], non_blocking=True)
+            L.computed.record(compute)
+        with torch.cuda.stream(self._d2h):
+            self._d2h.wait_event(L.computed)
+            for k in keys:
+                hb["out"][k].copy_(hb["dev_out"][k], non_blocking=True)
+            L.done.record(self._d2h)
+        return hb["out"]
 
     def lane_done(self, i):
         return self._lanes[i % self.slots].done
