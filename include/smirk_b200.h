@@ -88,7 +88,7 @@ typedef struct {
     int n_verts;               /* vertices of the incoming mesh (5023) */
     int n_mask;                /* rendered subset (1787 for the FLAME `face` mask; = n_verts for full head) */
     const int32_t* mask_ids;   /* [n_mask] vertex ids, order defines the sub-mesh numbering (renderer.py:71) */
-    int n_faces;               /* 3408 */
+    int n_faces;               /* 3408; must be < 65536 and a multiple of 4 (packed tile ranges are read 4 at a time) */
     const int32_t* faces;      /* [n_faces,3] indices into the sub-mesh (renderer.py:74) */
     int image_size;            /* 224 */
 } SmkRendererDesc;
@@ -122,7 +122,8 @@ typedef struct {
     const float* head_b[3];
     int n_shape;               /* 300 */
     int n_exp;                 /* 50 */
-    int precision;             /* 0 = fp32 CUDA-core GEMMs, 1 = TF32 tcgen05 GEMMs for the 1x1 convs */
+    int precision;             /* 0 = fp32 CUDA-core GEMMs, 1 = TF32 tcgen05 GEMMs for the 1x1 convs,
+                                  2 = 1 + inverted-residual blocks run expand-1x1 + depthwise-3x3 as one fused kernel */
 } SmkEncoderDesc;
 
 int smk_encoder_create(const SmkEncoderDesc* desc, SmkEncoder** out);
@@ -169,6 +170,11 @@ int smk_debug_conv_tc(const float* in, int ld_in, int B, int H, int W, int Cin, 
                       const float* bias, int N, int K, int mode, int relu, const float* res, int ld_res, int res_pad,
                       float* out, int ld_out, int store, void* stream);
 int smk_debug_reflect_halo(float* buf, int B, int H, int W, int C, void* stream);
+/*   smk_debug_conv3_sw: shifted-window TF32 tcgen05 3x3 conv (same argument meaning as smk_debug_conv_tc with
+ *                       mode 1 or 2 and store 0 or 2); use_base_offset selects the descriptor variant.          */
+int smk_debug_conv3_sw(const float* in, int ld_in, int B, int H, int W, int Cin, const float* wt, const float* scale,
+                       const float* bias, int N, int mode, int relu, const float* res, int ld_res, int res_pad,
+                       float* out, int ld_out, int store, int use_base_offset, void* stream);
 /*   smk_debug_xdw: fused expand-1x1 (TF32 tcgen05) + BN + ReLU + depthwise-3x3 (fp32) + BN + ReLU of a
  *                  MobileNetV3 inverted-residual block.  x [B,H,W,Cin] NHWC; w1t [mid][Cin]; wdw [9][mid];
  *                  out [B,ceil(H/stride),ceil(W/stride),mid]; TF-SAME padding.                            */

@@ -219,12 +219,12 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
         SMK_CHECK_CUDA(cudaEventRecord(h->fork, main_st));
         for (int s = 0; s < 2; ++s) SMK_CHECK_CUDA(cudaStreamWaitEvent(h->side[s], h->fork, 0));
     }
-    for (int i = 0; i < 3; ++i) {
+    int rc = 0;                                   // first error; the side streams are joined on every path
+    for (int i = 0; i < 3 && !rc; ++i) {
         const Backbone& bb = h->bb[i];
         cudaStream_t st = (i == 0 || !concurrent) ? main_st : h->side[i - 1];
         float* const* buf = bufs[i];
         float *x = buf[0], *y = buf[1], *e = buf[2], *d = buf[3];
-        int rc = 0;
         int res = 112;
         for (const Block& b : bb.blocks) {
             int ro = (res + b.stride - 1) / b.stride;
@@ -246,16 +246,16 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
             } else {
                 rc = pointwise(b.pw, x, B, res, res, true, nullptr, y, st);
             }
-            if (rc) return rc;
+            if (rc) break;
             std::swap(x, y);
             res = ro;
         }
-        rc = smk::gap_linear(x, B, res * res, bb.feat, bb.head_w, bb.head_b, bb.n_out, bb.codes, y, outs[i], st);
-        if (rc) return rc;
+        if (!rc) rc = smk::gap_linear(x, B, res * res, bb.feat, bb.head_w, bb.head_b, bb.n_out, bb.codes, y, outs[i], st);
     }
-    for (int s = 0; s < 2 && concurrent; ++s) {
-        SMK_CHECK_CUDA(cudaEventRecord(h->join[s], h->side[s]));
-        SMK_CHECK_CUDA(cudaStreamWaitEvent(main_st, h->join[s], 0));
+    for (int s = 0; s < 2 && concurrent; ++s) {   // join even after an error so a capturing stream is left consistent
+        cudaError_t e1 = cudaEventRecord(h->join[s], h->side[s]);
+        cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(main_st, h->join[s], 0) : e1;
+        if (!rc && e2 != cudaSuccess) { smk::set_error("smk_encoder_forward: stream join failed: %s", cudaGetErrorString(e2)); rc = (int)e2; }
     }
-    return 0;
+    return rc;
 }

@@ -357,10 +357,14 @@ int encode_im2col(CUtensorMap* map, const float* base, int B, int Hin, int Win, 
 template <int BN, int STAGES, int MINB>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * BKB) + 1024 + 256;
-    static bool configured = false;
-    if (!configured) {
+    // The attribute is per device and per function; set it once per (device, instantiation).  One bit per
+    // device ordinal; a benign race (two threads setting it twice) is harmless.
+    static unsigned long long configured_mask = 0;
+    int dev = 0;
+    SMK_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !(configured_mask & (1ull << dev))) {
         SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        if (dev < 64) configured_mask |= 1ull << dev;
     }
     dim3 grid(cdiv(a.M, BM), cdiv(a.N, BN));
     gemm_tc_kernel<BN, STAGES, MINB><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, a);

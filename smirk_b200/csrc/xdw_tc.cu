@@ -358,11 +358,13 @@ int xdw_conv(const XdwConv& p, cudaStream_t st) {
     a.tiles_x = cdiv(Wo, TO); a.tiles_y = cdiv(Ho, TO);
     a.scale1 = p.scale1; a.bias1 = p.bias1; a.wdw = p.wdw; a.scale2 = p.scale2; a.bias2 = p.bias2; a.out = p.out; a.round_out = p.round_out;
     constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + E_BYTES + 1024 + 256;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured_mask = 0;       // per-device attribute, see gemm_tc.cu
+    int dev = 0;
+    SMK_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !(configured_mask & (1ull << dev))) {
         SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        if (dev < 64) configured_mask |= 1ull << dev;
     }
     {
         const double px_in = (double)p.B * p.H * p.W, px_out = (double)p.B * Ho * Wo;
