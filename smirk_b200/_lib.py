@@ -96,7 +96,7 @@ def lib():
     L.smk_debug_conv_f32.argtypes = [vp, i, i, i, i, i, vp, vp, vp, i, i, i, i, vp, i, vp, i, i, vp]
     L.smk_debug_conv_tc.argtypes = [vp, i, i, i, i, i, vp, vp, vp, i, i, i, i, vp, i, i, vp, i, i, vp]
     L.smk_debug_reflect_halo.argtypes = [vp, i, i, i, i, vp]
-    L.smk_debug_conv3_sw.argtypes = [vp, i, i, i, i, i, vp, vp, vp, i, i, i, vp, i, i, vp, i, i, i, vp]
+    L.smk_debug_conv3_sw.argtypes = [vp, i, i, i, i, i, vp, vp, vp, i, i, i, vp, i, i, vp, i, i, vp]
     L.smk_debug_xdw.argtypes = [vp, i, i, i, i, vp, vp, vp, i, vp, vp, vp, i, i, vp, vp]
     if L.smk_version() != 100:
         raise RuntimeError("smirk_b200: library/header version mismatch (%d)" % L.smk_version())

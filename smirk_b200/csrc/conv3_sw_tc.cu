@@ -10,8 +10,8 @@
 //   patch         (TH + 2) x PW pixels x 32 channels, one 4-D tiled TMA box (out-of-image halo = zero padding),
 //                 rows of 128 bytes in SWIZZLE_128B order, row index r = py * PW + px
 //   tap (dy,dx)   the A operand is the 128 consecutive patch rows starting at row dy*PW + dx: the UMMA
-//                 descriptor's start address moves by whole 128-byte rows and carries the swizzle phase in its
-//                 base-offset field.  GEMM row m is output pixel (m / PW, m % PW); the two columns m % PW >= TW
+//                 descriptor's start address simply moves by whole 128-byte rows (the tensor core takes the swizzle
+//                 phase from the address itself).  GEMM row m is output pixel (m / PW, m % PW); the two columns m % PW >= TW
 //                 of each row wrap into the halo and are simply not stored (94 % / 88 % of the MMA rows are useful).
 //   weights       [N][9*Cin] K-major, one BN x 32 box per (tap, chunk) through a small ring of their own.
 //
@@ -33,7 +33,6 @@ struct SwArgs {
     int N, Cin, nchunks;       // Cout, Cin, Cin / 32
     int origin;                // -1: zero padding by TMA out-of-bounds fill; 0: input buffer is already padded by 1
     int n_tiles_n;             // blockIdx.z = img * n_tiles_n + n_tile
-    int use_base_offset;       // descriptor base-offset field on (1) / off (0) for row-shifted tap views
     const float* scale; const float* bias;
     const float* res; int ld_res; int res_pad;
     int relu;
@@ -111,11 +110,9 @@ conv3_sw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                     const uint32_t a_tap = a_base + (uint32_t)(((tap / 3) * PW + (tap % 3)) * 128);
                     const uint32_t b_tap = smem_u32(sB + s * B_BYTES);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        uint64_t da = make_smem_desc(a_tap + k * 32);
-                        if (!a.use_base_offset) da &= ~((uint64_t)7 << 49);
-                        umma_tf32(tmem_base, da, make_smem_desc(b_tap + k * 32), IDESC, (c | tap | k) != 0 ? 1u : 0u);
-                    }
+                    for (int k = 0; k < 4; ++k)
+                        umma_tf32(tmem_base, make_smem_desc(a_tap + k * 32), make_smem_desc(b_tap + k * 32), IDESC,
+                                  (c | tap | k) != 0 ? 1u : 0u);
                     tcgen05_commit(&b_empty[s]);
                 }
                 tcgen05_commit(&a_empty[sa]);
@@ -219,7 +216,7 @@ int launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const SwArgs& a, dim3
 }  // namespace
 
 // p uses TcConv semantics with mode 1 (zero padding 1) or 2 (input already padded by 1), store 0 or 2.
-int conv3_sw(const TcConv& p, int use_base_offset, cudaStream_t st) {
+int conv3_sw(const TcConv& p, cudaStream_t st) {
     if (int rc = load_encoder()) return rc;
     SMK_REQUIRE((p.mode == 1 || p.mode == 2) && p.Cin % 32 == 0 && p.K == 9 * p.Cin, "conv3_sw: needs a 3x3 conv with Cin %% 32 == 0");
     SMK_REQUIRE(p.store == 0 || p.store == 2, "conv3_sw: store must be 0 or 2");
@@ -249,7 +246,7 @@ int conv3_sw(const TcConv& p, int use_base_offset, cudaStream_t st) {
     }
     SwArgs a{};
     a.H = p.H; a.W = p.W; a.N = p.N; a.Cin = p.Cin; a.nchunks = p.Cin / 32; a.origin = p.mode == 2 ? 0 : -1;
-    a.n_tiles_n = cdiv(p.N, BN); a.use_base_offset = use_base_offset;
+    a.n_tiles_n = cdiv(p.N, BN);
     a.scale = p.scale; a.bias = p.bias; a.res = p.res; a.ld_res = p.ld_res; a.res_pad = p.res_pad; a.relu = p.relu;
     a.out = p.out; a.ld_out = p.ld_out; a.store = p.store; a.round_out = p.round_out;
     dim3 grid(cdiv(p.W, TW), cdiv(p.H, TH), p.B * a.n_tiles_n);
@@ -273,9 +270,9 @@ int conv3_sw(const TcConv& p, int use_base_offset, cudaStream_t st) {
 
 extern "C" int smk_debug_conv3_sw(const float* in, int ld_in, int B, int H, int W, int Cin, const float* wt, const float* scale,
                                   const float* bias, int N, int mode, int relu, const float* res, int ld_res, int res_pad,
-                                  float* out, int ld_out, int store, int use_base_offset, void* stream) {
+                                  float* out, int ld_out, int store, void* stream) {
     smk::TcConv p{};
     p.in = in; p.ld_in = ld_in; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.wt = wt; p.scale = scale; p.bias = bias; p.N = N; p.K = 9 * Cin;
     p.mode = mode; p.relu = relu; p.res = res; p.ld_res = ld_res; p.res_pad = res_pad; p.out = out; p.ld_out = ld_out; p.store = store;
-    return smk::conv3_sw(p, use_base_offset, (cudaStream_t)stream);
+    return smk::conv3_sw(p, (cudaStream_t)stream);
 }

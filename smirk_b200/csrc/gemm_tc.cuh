@@ -22,6 +22,6 @@ int tc_init();                                              // resolves the driv
 int tc_conv(const TcConv& p, cudaStream_t st);
 int reflect_halo(float* buf, int B, int H, int W, int C, cudaStream_t st);
 // Shifted-window variant for 3x3 convs (conv3_sw_tc.cu): one patch load per channel chunk, nine tap views.
-int conv3_sw(const TcConv& p, int use_base_offset, cudaStream_t st);
+int conv3_sw(const TcConv& p, cudaStream_t st);
 
 }  // namespace smk

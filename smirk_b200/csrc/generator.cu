@@ -16,6 +16,7 @@
 #include "nn_kernels.cuh"
 #include "gemm_tc.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -173,6 +174,12 @@ int conv3(const SmkGenerator* h, const Conv3& c, const float* in, int ld_in, int
         p.in = in; p.ld_in = ld_in; p.B = B; p.H = S; p.W = S; p.Cin = c.cin_p; p.wt = c.wt; p.scale = c.scale; p.bias = c.bias;
         p.N = c.cout; p.K = 9 * c.cin_p; p.mode = refl ? 2 : 1; p.relu = relu ? 1 : 0;
         p.res = res; p.ld_res = c.cout; p.res_pad = res_pad; p.out = out; p.ld_out = ld_out; p.store = store; p.round_out = 1;
+        // Wide, shallow layers (N <= 64: the 224^2 / 112^2 levels) are bound by the nine-fold im2col re-read of
+        // the activations: they take the shifted-window kernel (one patch load per channel chunk).  Deep layers
+        // are dominated by weight traffic and keep the im2col kernel.  SMK_CONV3_SW=0/1 forces either path.
+        static const int force = []() { const char* e = getenv("SMK_CONV3_SW"); return e ? atoi(e) : -1; }();
+        const bool use_sw = force >= 0 ? force != 0 : c.cout <= 64;
+        if (use_sw) return smk::conv3_sw(p, st);
         return smk::tc_conv(p, st);
     }
     ConvProblem p{};
