@@ -1,6 +1,7 @@
 // Error channel + version for the smirk_b200 C ABI.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace smk {
 static thread_local char g_err[512] = "";
@@ -38,6 +39,7 @@ void prof_begin(const char* tag, double bytes, double flops, cudaStream_t st) {
     g_pending = true; g_pending_stream = st;
 }
 bool profiling() { return g_prof; }
+bool pdl_enabled() { static const bool on = []() { const char* e = getenv("SMK_PDL"); return !e || atoi(e) != 0; }(); return on; }
 void prof_end() {
     if (!g_prof || !g_pending) return;
     cudaEventRecord(g_entries.back().b, g_pending_stream);

@@ -76,6 +76,7 @@ conv3_sw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -208,7 +209,7 @@ int launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const SwArgs& a, dim3
         SMK_CHECK_CUDA(cudaFuncSetAttribute(conv3_sw_kernel<BN, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev < 64) configured_mask |= 1ull << dev;
     }
-    conv3_sw_kernel<BN, PW><<<grid, NUM_THREADS, smem, st>>>(tmX, tmW, a);
+    SMK_LAUNCH((conv3_sw_kernel<BN, PW>), dim3(grid), dim3(NUM_THREADS), smem, st, tmX, tmW, a);
     SMK_CHECK_LAUNCH();
     return 0;
 }

@@ -73,6 +73,7 @@ flame_pose_kernel(FlameDev d, const float* __restrict__ betas, const float* __re
                   float* __restrict__ joints_out /*[B][5][3] or null*/, int32_t* __restrict__ dyn_out /*[B]*/) {
     __shared__ float sJ[15];
     __shared__ float sR[kJ][9];
+    smk::pdl_sync();
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* beta = betas + (size_t)b * d.L;
     // J = J0 + JS * beta : 15 dot products of length L, one warp per row (lbs.py:188 pre-contracted)
@@ -153,6 +154,7 @@ flame_verts_kernel(FlameDev d, const float* __restrict__ betas, const float* __r
     float* sE = sA + BT * 60;               // [BT][2]
     const int b0 = blockIdx.y * BT;
     const int tid = threadIdx.x;
+    smk::pdl_sync();
     for (int i = tid; i < d.L * BT; i += 128) {
         int l = i / BT, t = i % BT;
         int b = min(b0 + t, B - 1);
@@ -257,6 +259,7 @@ flame_landmarks_kernel(FlameDev d, const float* __restrict__ verts, const int32_
     const int n_fan = d.n_dyn + d.n_static;
     const int total = n_fan + d.n_full + d.n_mp;
     const float* vb = verts + (size_t)b * d.V * 3;
+    smk::pdl_sync();
     const int row = dyn_idx[b];
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         int f; const float* bc; float* out;
@@ -352,7 +355,7 @@ static int launch_verts(const FlameDev& d, const float* betas, const float* eyel
     dim3 grid(smk::cdiv(d.V, 32), smk::cdiv(B, BT));          // 32 vertices x 4 k-slices per CTA
     SMK_TAG("flame_verts", 4.0 * ((double)(d.L + kPF) * d.Mp + 6.0 * d.Mp + 5.0 * d.V + (double)B * (d.L + 3.0 * d.V + 98)),
             2.0 * B * (3.0 * d.V * (d.L + kPF) + (double)d.V * (60 + 12 + 6)), st);
-    flame_verts_kernel<BT><<<grid, 128, smem, st>>>(d, betas, eyelid, A, pf, B, verts);
+    SMK_LAUNCH((flame_verts_kernel<BT>), dim3(grid), dim3(128), smem, st, d, betas, eyelid, A, pf, B, verts);
     SMK_CHECK_LAUNCH();
     return 0;
 }
@@ -371,7 +374,7 @@ extern "C" int smk_flame_forward(const SmkFlame* h, const float* betas, const fl
     int32_t* dyn = w.take<int32_t>(B);
     const FlameDev& d = h->d;
     SMK_TAG("flame_pose", 4.0 * (15.0 * d.L + (double)B * (d.L + 15 + 60 + kPF + 16)), 2.0 * B * 15.0 * d.L, st);
-    flame_pose_kernel<<<B, 128, 0, st>>>(d, betas, full_pose, B, A, pf, joints, dyn);
+    SMK_LAUNCH(flame_pose_kernel, dim3(B), dim3(128), 0, st, d, betas, full_pose, B, A, pf, joints, dyn);
     SMK_CHECK_LAUNCH();
     int rc;
     if (B >= 96) rc = launch_verts<8>(d, betas, eyelid, A, pf, B, verts, st);
@@ -380,7 +383,7 @@ extern "C" int smk_flame_forward(const SmkFlame* h, const float* betas, const fl
     else rc = launch_verts<1>(d, betas, eyelid, A, pf, B, verts, st);
     if (rc) return rc;
     SMK_TAG("flame_landmarks", 4.0 * B * 241.0 * (9 + 3 + 3 + 4), 2.0 * B * 241 * 9, st);
-    flame_landmarks_kernel<<<B, 256, 0, st>>>(d, verts, dyn, B, lmk_fan, lmk_fan3d, lmk_mp);
+    SMK_LAUNCH(flame_landmarks_kernel, dim3(B), dim3(256), 0, st, d, verts, dyn, B, lmk_fan, lmk_fan3d, lmk_mp);
     SMK_CHECK_LAUNCH();
     if (dyn_idx) SMK_CHECK_CUDA(cudaMemcpyAsync(dyn_idx, dyn, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
     return 0;

@@ -33,6 +33,7 @@ constexpr int BK = 32;
 constexpr int UMMA_K = 8;                 // tf32
 constexpr int A_STAGE_BYTES = BM * BKB;   // 16 KiB
 constexpr int NUM_THREADS = 192;
+constexpr int SLAB_BYTES = 4 * 4096;      // epilogue staging: 32 rows x 128 B per epilogue warp
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -42,6 +43,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -113,6 +117,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 
 struct TcArgs {
     int M, N, nkb;                 // nkb = number of 32-wide k-blocks
+    int tiles_n, n_tiles;          // column tiles per row of tiles, total tiles (tile t -> row tile t / tiles_n)
     int mode;                      // 0 = 2-D tiled A; 1 = im2col A
     int H, W;                      // output spatial dims (im2col tile origin decode; shuffle / padded stores)
     int cpb;                       // k-blocks per filter tap (Cin / 32) for im2col
@@ -125,30 +130,38 @@ struct TcArgs {
     int round_out;                 // 1: round the stored activations to TF32 (round-to-nearest) for the next tensor-core layer
 };
 
-template <int BN, int STAGES, int MINB>
+template <int BN, int STAGES, int MINB, bool PERSIST>
 __global__ void __launch_bounds__(NUM_THREADS, MINB)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+    // Output tiles (128 rows x BN columns) are strided over the grid.
+    //   PERSIST = true : grid = resident CTAs; the smem ring runs across tile boundaries and the accumulator is
+    //                    double-buffered in TMEM, so the TMA loads and MMAs of tile i+1 overlap the epilogue of
+    //                    tile i.  Wins for the deep-K 3x3 convolutions (measured, profiles/r01_gemm_tc_persist.txt).
+    //   PERSIST = false: grid = tiles, one tile per CTA, the epilogue staging slab aliases the (by then idle)
+    //                    first ring stage and TMEM holds one accumulator: smaller footprint -> 3-5 CTAs per SM,
+    //                    which is what the shallow-K streaming 1x1 layers want (more epilogue warps in flight).
     constexpr int B_STAGE_BYTES = BN * BKB;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t TMEM_COLS = PERSIST ? 2 * BN : BN;   // 32..256: powers of two
     constexpr uint32_t IDESC = make_idesc(BM, BN);
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B; offset arithmetic keeps the shared address space visible to the
     // compiler (LDS/STS for the staging slab instead of generic LD/ST).
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint8_t* slabs = PERSIST ? smem + STAGES * STAGE_BYTES : smem;      // 4 x 4 KiB epilogue staging, one per epilogue warp
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + (PERSIST ? SLAB_BYTES : 0));
     uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* acc_full = empty + STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -159,53 +172,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();                                // barriers, tensor maps and TMEM are set up; now wait for the producer layer
 
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            int q0 = 0, p0 = 0, img = 0;
-            if (a.mode == 1) { int hw = a.H * a.W; img = m0 / hw; int r = m0 - img * hw; p0 = r / a.W; q0 = r - p0 * a.W; }
-            for (int kb = 0; kb < a.nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
-                uint8_t* sa = smem + s * STAGE_BYTES;
-                uint8_t* sb = sa + A_STAGE_BYTES;
-                mbar_expect_tx(&full[s], (uint32_t)STAGE_BYTES);
-                if (a.mode == 0) {
-                    tma_load_2d(&tmA, sa, &full[s], kb * BK, m0);
-                } else {
-                    int tap = kb / a.cpb, ch = kb - tap * a.cpb;
-                    int r = tap / 3, sx = tap - r * 3;
-                    tma_load_im2col(&tmA, sa, &full[s], ch * BK, q0 + a.lc, p0 + a.lc, img, (uint16_t)sx, (uint16_t)r);
+            int it = 0;
+            for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+                const int tm = t / a.tiles_n, tn = t - tm * a.tiles_n;
+                const int m0 = tm * BM, n0 = tn * BN;
+                int q0 = 0, p0 = 0, img = 0;
+                if (a.mode == 1) { int hw = a.H * a.W; img = m0 / hw; int r = m0 - img * hw; p0 = r / a.W; q0 = r - p0 * a.W; }
+                for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+                    uint8_t* sa = smem + s * STAGE_BYTES;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    mbar_expect_tx(&full[s], (uint32_t)STAGE_BYTES);
+                    if (a.mode == 0) {
+                        tma_load_2d(&tmA, sa, &full[s], kb * BK, m0);
+                    } else {
+                        int tap = kb / a.cpb, ch = kb - tap * a.cpb;
+                        int r = tap / 3, sx = tap - r * 3;
+                        tma_load_im2col(&tmA, sa, &full[s], ch * BK, q0 + a.lc, p0 + a.lc, img, (uint16_t)sx, (uint16_t)r);
+                    }
+                    tma_load_2d(&tmB, sb, &full[s], kb * BK, n0);
                 }
-                tma_load_2d(&tmB, sb, &full[s], kb * BK, n0);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer =====
-            for (int kb = 0; kb < a.nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(&full[s], ph);
+            int it = 0, tc = 0;
+            for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++tc) {
+                const int buf = tc & 1;
+                mbar_wait(&acc_empty[buf], ((uint32_t)(tc >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
                 tcgen05_fence_after();
-                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-                const uint32_t sb = sa + A_STAGE_BYTES;
+                for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    uint64_t da = make_smem_desc(sa + k * UMMA_K * 4);
-                    uint64_t db = make_smem_desc(sb + k * UMMA_K * 4);
-                    umma_tf32(tmem_base, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        uint64_t da = make_smem_desc(sa + k * UMMA_K * 4);
+                        uint64_t db = make_smem_desc(sb + k * UMMA_K * 4);
+                        umma_tf32(tmem_base + (uint32_t)(buf * BN), da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    tcgen05_commit(&empty[s]);          // frees this smem stage once the MMAs above have read it
                 }
-                tcgen05_commit(&empty[s]);          // frees this smem stage once the MMAs above have read it
+                tcgen05_commit(&acc_full[buf]);         // accumulator complete
             }
-            tcgen05_commit(tmem_full);              // accumulator complete
         }
     } else {
         // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-        mbar_wait(tmem_full, 0);
-        tcgen05_fence_after();
         // Two phases per 32-column chunk, both private to the warp (it owns TMEM lanes / tile rows
         // [32*quarter, +32)), so only __syncwarp separates them:
         //   1. lane = row: tcgen05.ld 32 accumulator columns and park them in a 32 x 128-byte staging
@@ -213,64 +234,75 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         //   2. 8 lanes per row, 4 rows per instruction: read the slab back transposed, apply
         //      scale/bias (+residual) (+ReLU) (+TF32 rounding) and store — every global access of the
         //      warp now covers whole 128-byte lines of 4 output rows instead of 16 bytes of 32 rows.
-        // The pipeline stages are idle by now (tmem_full fires after the last MMA has read them), so
-        // stage 0's A slab (16 KiB) doubles as the staging buffer: 4 KiB per epilogue warp.
         const int quarter = warp & 3;
-        uint8_t* slab = smem + quarter * 4096;
+        uint8_t* slab = slabs + quarter * 4096;
         const int sub = lane >> 3, jj = lane & 7;              // phase-2 role: row-in-group, 16-byte chunk
-        int opix[8], rpix[8];                                  // destination / residual pixel of my 8 phase-2 rows (-1: past M)
+        int tc = 0;
+        for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++tc) {
+            const int tm = t / a.tiles_n, tn = t - tm * a.tiles_n;
+            const int m0 = tm * BM, n0 = tn * BN;
+            const int buf = tc & 1;
+            int opix[8], rpix[8];                              // destination / residual pixel of my 8 phase-2 rows (-1: past M)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int m = m0 + quarter * 32 + 4 * i + sub;
-            int o = -1, r = -1;
-            if (m < a.M) {
-                o = r = m;
-                if (a.store != 0 || a.res_pad) {
-                    const int hw = a.H * a.W, b = m / hw, rem = m - b * hw, h = rem / a.W, w = rem - h * a.W;
-                    const int padded = (b * (a.H + 2) + h + 1) * (a.W + 2) + w + 1;
-                    if (a.store == 2) o = padded;
-                    else if (a.store == 1) o = (b * (2 * a.H) + 2 * h) * (2 * a.W) + 2 * w;
-                    if (a.res_pad) r = padded;
-                }
-            }
-            opix[i] = o; rpix[i] = r;
-        }
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);     // warp-collective
-            const int n = n0 + c0;
-            if (n >= a.N) break;                               // warp-uniform
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            __syncwarp();
-            const int nc = n + jj * 4;                         // my 4 columns
-            if (nc < a.N) {
-                const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + nc));
-                const float4 bi = __ldg(reinterpret_cast<const float4*>(a.bias + nc));
-                int col = nc, pix_off = 0;
-                if (a.store == 1) {                            // ConvTranspose2d k2 s2: n = (dy*2+dx)*Cout + co
-                    const int cout = a.N >> 2, q = nc / cout;
-                    col = nc - q * cout; pix_off = (q >> 1) * (2 * a.W) + (q & 1);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (opix[i] < 0) continue;
-                    const int r = 4 * i + sub;
-                    const float4 x = *reinterpret_cast<const float4*>(slab + r * 128 + ((jj ^ (r & 7)) << 4));
-                    float4 o;
-                    o.x = fmaf(x.x, sc.x, bi.x); o.y = fmaf(x.y, sc.y, bi.y); o.z = fmaf(x.z, sc.z, bi.z); o.w = fmaf(x.w, sc.w, bi.w);
-                    if (a.res) {
-                        const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.res + (size_t)rpix[i] * a.ld_res + nc));
-                        o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+            for (int i = 0; i < 8; ++i) {
+                const int m = m0 + quarter * 32 + 4 * i + sub;
+                int o = -1, r = -1;
+                if (m < a.M) {
+                    o = r = m;
+                    if (a.store != 0 || a.res_pad) {
+                        const int hw = a.H * a.W, b = m / hw, rem = m - b * hw, h = rem / a.W, w = rem - h * a.W;
+                        const int padded = (b * (a.H + 2) + h + 1) * (a.W + 2) + w + 1;
+                        if (a.store == 2) o = padded;
+                        else if (a.store == 1) o = (b * (2 * a.H) + 2 * h) * (2 * a.W) + 2 * w;
+                        if (a.res_pad) r = padded;
                     }
-                    if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                    if (a.round_out) { o.x = smk::round_tf32(o.x); o.y = smk::round_tf32(o.y); o.z = smk::round_tf32(o.z); o.w = smk::round_tf32(o.w); }
-                    *reinterpret_cast<float4*>(a.out + (size_t)(opix[i] + pix_off) * a.ld_out + col) = o;
                 }
+                opix[i] = o; rpix[i] = r;
             }
-            __syncwarp();
+            mbar_wait(&acc_full[buf], (uint32_t)(tc >> 1) & 1u);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int n = n0 + c0;
+                if (n >= a.N) break;                           // warp-uniform
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c0), v);     // warp-collective
+                if (c0 + 32 >= BN || n + 32 >= a.N) {          // last read of this accumulator: hand it back to the MMA warp
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+                const int nc = n + jj * 4;                     // my 4 columns
+                if (nc < a.N) {
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + nc));
+                    const float4 bi = __ldg(reinterpret_cast<const float4*>(a.bias + nc));
+                    int col = nc, pix_off = 0;
+                    if (a.store == 1) {                        // ConvTranspose2d k2 s2: n = (dy*2+dx)*Cout + co
+                        const int cout = a.N >> 2, q = nc / cout;
+                        col = nc - q * cout; pix_off = (q >> 1) * (2 * a.W) + (q & 1);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (opix[i] < 0) continue;
+                        const int r = 4 * i + sub;
+                        const float4 x = *reinterpret_cast<const float4*>(slab + r * 128 + ((jj ^ (r & 7)) << 4));
+                        float4 o;
+                        o.x = fmaf(x.x, sc.x, bi.x); o.y = fmaf(x.y, sc.y, bi.y); o.z = fmaf(x.z, sc.z, bi.z); o.w = fmaf(x.w, sc.w, bi.w);
+                        if (a.res) {
+                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.res + (size_t)rpix[i] * a.ld_res + nc));
+                            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                        }
+                        if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        if (a.round_out) { o.x = smk::round_tf32(o.x); o.y = smk::round_tf32(o.y); o.z = smk::round_tf32(o.z); o.w = smk::round_tf32(o.w); }
+                        *reinterpret_cast<float4*>(a.out + (size_t)(opix[i] + pix_off) * a.ld_out + col) = o;
+                    }
+                }
+                __syncwarp();
+            }
         }
         tcgen05_fence_before();
     }
@@ -284,6 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---- reflection halo of a [B, H+2, W+2, C] buffer whose interior has been written -------------------
 __global__ void __launch_bounds__(256)
 reflect_halo_kernel(float* __restrict__ buf, int B, int H, int W, int C) {
+    pdl_sync();
     const int Hp = H + 2, Wp = W + 2, C4 = C >> 2;
     const int halo = 2 * Wp + 2 * H;                       // halo pixels per image
     long total = (long)B * halo * C4;
@@ -354,20 +387,25 @@ int encode_im2col(CUtensorMap* map, const float* base, int B, int Hin, int Win, 
     return 0;
 }
 
-template <int BN, int STAGES, int MINB>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
-    constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * BKB) + 1024 + 256;
+template <int BN, int STAGES, int MINB, bool PERSIST>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a_in, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * BKB) + (PERSIST ? SLAB_BYTES : 0) + 1024 + 256;
+    static_assert(MINB * (smem + 1024) <= 228 * 1024, "shared memory budget of MINB resident CTAs");
+    static_assert(MINB * (PERSIST ? 2 : 1) * BN <= 512, "TMEM budget of MINB resident CTAs");
     // The attribute is per device and per function; set it once per (device, instantiation).  One bit per
     // device ordinal; a benign race (two threads setting it twice) is harmless.
     static unsigned long long configured_mask = 0;
     int dev = 0;
     SMK_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !(configured_mask & (1ull << dev))) {
-        SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, MINB, PERSIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev < 64) configured_mask |= 1ull << dev;
     }
-    dim3 grid(cdiv(a.M, BM), cdiv(a.N, BN));
-    gemm_tc_kernel<BN, STAGES, MINB><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, a);
+    TcArgs a = a_in;
+    a.tiles_n = cdiv(a.N, BN);
+    a.n_tiles = cdiv(a.M, BM) * a.tiles_n;
+    dim3 grid((unsigned)(PERSIST ? std::min(a.n_tiles, MINB * 148) : a.n_tiles));
+    SMK_LAUNCH((gemm_tc_kernel<BN, STAGES, MINB, PERSIST>), dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB, a);
     SMK_CHECK_LAUNCH();
     return 0;
 }
@@ -414,20 +452,30 @@ int tc_conv(const TcConv& p, cudaStream_t st) {
                 4.0 * ((double)M * cin_eff + (double)p.K * p.N + (double)M * p.N * (p.res ? 2 : 1) + 2.0 * p.N),
                 2.0 * (double)M * p.N * p.K, st);
     }
+    if (deep_small && BN == 32) return launch<32, 8, 1, false>(tmA, tmB, a, st);
+    if (deep_small && BN == 64) return launch<64, 8, 1, false>(tmA, tmB, a, st);
+    static const int persist_mode = []() { const char* e = getenv("SMK_TC_PERSIST"); return e ? atoi(e) : -1; }();   // -1 auto, 0 never, 1 always
+    const long n_tiles = (long)cdiv(M, BM) * cdiv(p.N, BN);
+    // 3x3 convolutions (deep K): persistent CTAs for the narrow-N layers and for the few-tile 14x14 layers;
+    // the wide-N layers are bound by the shared-memory fill rate either way and keep two single-tile CTAs per SM.
+    const bool persist = persist_mode >= 0 ? persist_mode != 0 : (p.mode != 0 && (BN <= 64 || n_tiles <= 2 * 148));
+    if (persist) {
+        if (BN == 32) return launch<32, 4, 2, true>(tmA, tmB, a, st);
+        if (BN == 64) return launch<64, 3, 2, true>(tmA, tmB, a, st);
+        return a.nkb > 8 ? launch<128, 5, 1, true>(tmA, tmB, a, st) : launch<128, 2, 2, true>(tmA, tmB, a, st);
+    }
     // Shallow-K layers (the encoder's 1x1 convs) are HBM-bound: a 2-stage ring keeps the footprint small so
     // 3-5 CTAs share an SM and hide each other's prologue/epilogue; deep-K layers get a deeper ring.
     const bool shallow = a.nkb <= 2;
-    if (deep_small && BN == 32) return launch<32, 8, 1>(tmA, tmB, a, st);
-    if (deep_small && BN == 64) return launch<64, 8, 1>(tmA, tmB, a, st);
-    if (BN == 32) return shallow ? launch<32, 2, 5>(tmA, tmB, a, st) : launch<32, 4, 2>(tmA, tmB, a, st);
-    if (BN == 64) return shallow ? launch<64, 2, 4>(tmA, tmB, a, st) : launch<64, 4, 2>(tmA, tmB, a, st);
-    return shallow ? launch<128, 2, 3>(tmA, tmB, a, st) : launch<128, 3, 2>(tmA, tmB, a, st);
+    if (BN == 32) return shallow ? launch<32, 2, 5, false>(tmA, tmB, a, st) : launch<32, 4, 2, false>(tmA, tmB, a, st);
+    if (BN == 64) return shallow ? launch<64, 2, 4, false>(tmA, tmB, a, st) : launch<64, 4, 2, false>(tmA, tmB, a, st);
+    return shallow ? launch<128, 2, 3, false>(tmA, tmB, a, st) : launch<128, 3, 2, false>(tmA, tmB, a, st);
 }
 
 int reflect_halo(float* buf, int B, int H, int W, int C, cudaStream_t st) {
     long total = (long)B * (2 * (W + 2) + 2 * H) * (C / 4);
     SMK_TAG("reflect_halo", 8.0 * (double)total * 4, 0.0, st);
-    reflect_halo_kernel<<<(int)std::min<long>((total + 255) / 256, 148L * 8), 256, 0, st>>>(buf, B, H, W, C);
+    SMK_LAUNCH(reflect_halo_kernel, dim3((int)std::min<long>((total + 255) / 256, 148L * 8)), dim3(256), 0, st, buf, B, H, W, C);
     SMK_CHECK_LAUNCH();
     return 0;
 }

@@ -22,6 +22,7 @@ conv_gemm_kernel(ConvProblem p, int M) {
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     const int HW = p.H * p.W;
+    pdl_sync();
 
     // per-thread A rows: r = tid/4 + 64*j, k-quad kq = tid%4
     const int kq = tid & 3;
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(256)
 dwconv3x3_kernel(const float* __restrict__ in, int B, int H, int W, int C, int stride, int pad, int Ho, int Wo,
                  const float* __restrict__ w9c, const float* __restrict__ scale, const float* __restrict__ bias,
                  float* __restrict__ out) {
+    pdl_sync();
     const int C4 = C >> 2;
     const long total = (long)B * Ho * Wo * C4;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -180,6 +182,7 @@ dwconv3x3_px4_kernel(const float* __restrict__ in, int B, int H, int W, int C, i
     constexpr int PX = 4, NC = 3 + (PX - 1) * STRIDE;
     const int C4 = C >> 2, WG = (Wo + PX - 1) / PX;
     const long total = (long)B * Ho * WG * C4;
+    pdl_sync();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         int c4 = (int)(i % C4); long t = i / C4;
         int wg = (int)(t % WG); t /= WG; int oh = (int)(t % Ho); int b = (int)(t / Ho);
@@ -229,6 +232,7 @@ dwconv3x3_px4_kernel(const float* __restrict__ in, int B, int H, int W, int C, i
 __global__ void __launch_bounds__(256)
 gap_kernel(const float* __restrict__ feat, int HW, int C, float* __restrict__ pooled) {
     __shared__ float part[4][64];
+    pdl_sync();
     const int b = blockIdx.x, c = blockIdx.y * 64 + (threadIdx.x & 63), pl = threadIdx.x >> 6;
     float s = 0.f;
     if (c < C) {
@@ -245,6 +249,7 @@ gap_kernel(const float* __restrict__ feat, int HW, int C, float* __restrict__ po
 __global__ void __launch_bounds__(256)
 head_linear_kernel(const float* __restrict__ pooled, int C, const float* __restrict__ w, const float* __restrict__ bias,
                    int n_out, const uint8_t* __restrict__ codes, float* __restrict__ out) {
+    pdl_sync();
     const int b = blockIdx.x, lane = threadIdx.x & 31, o = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (o >= n_out) return;
     const float* wr = w + (size_t)o * C;
@@ -272,6 +277,7 @@ stem_conv_kernel(const float* __restrict__ img, int B, int H, int W, int Ho, int
     for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) sw[i] = w[i];
     if (threadIdx.x < 16) { ss[threadIdx.x] = scale[threadIdx.x]; sb[threadIdx.x] = bias[threadIdx.x]; }
     __syncthreads();
+    pdl_sync();
     long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= (long)B * Ho * Wo) return;
     int ow = (int)(pix % Wo); long t = pix / Wo; int oh = (int)(t % Ho); int b = (int)(t / Ho);
@@ -319,6 +325,7 @@ stem_conv3_kernel(const float* __restrict__ img, int B, int H, int W, int Ho, in
     const int oh = blockIdx.x % Ho, b = blockIdx.x / Ho;
     for (int i = threadIdx.x; i < 27 * 48; i += blockDim.x) { int tap = i / 48, gc = i % 48; sw[i] = p.w[gc / 16][tap * 16 + gc % 16]; }
     if (threadIdx.x < 48) { ss[threadIdx.x] = p.scale[threadIdx.x / 16][threadIdx.x % 16]; sb[threadIdx.x] = p.bias[threadIdx.x / 16][threadIdx.x % 16]; }
+    pdl_sync();                                    // weights are constants; the image and the outputs are not
     {   // stage rows: element iw of row (c,ky) lands at sin_[c*3+ky][4 + iw] so 16-byte stores stay aligned; halo columns zeroed
         const int W4 = W >> 2;
         for (int i = threadIdx.x; i < 9 * W4; i += blockDim.x) {
@@ -367,6 +374,7 @@ __global__ void __launch_bounds__(256)
 maxpool2x2_kernel(const float* __restrict__ in, int ld_in, int B, int H, int W, int C, float* __restrict__ out) {
     const int Ho = H >> 1, Wo = W >> 1, C4 = C >> 2;
     const long total = (long)B * Ho * Wo * C4;
+    pdl_sync();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         int c4 = (int)(i % C4); long pix = i / C4;
         int ow = (int)(pix % Wo); long t = pix / Wo; int oh = (int)(t % Ho); int b = (int)(t / Ho);
@@ -382,6 +390,7 @@ maxpool2x2_kernel(const float* __restrict__ in, int ld_in, int B, int H, int W, 
 
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_pad_kernel(const float* __restrict__ in, int B, int C, int HW, int Cp, float* __restrict__ out) {
+    pdl_sync();
     long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= (long)B * HW) return;
     int b = (int)(pix / HW); int r = (int)(pix - (long)b * HW);
@@ -396,6 +405,7 @@ conv1x1_sigmoid_kernel(const float* __restrict__ in, int B, int HW, int Cin, con
     for (int i = threadIdx.x; i < Cin * Cout; i += blockDim.x) sw[i] = w[i];
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[Cin * Cout + i] = bias[i];
     __syncthreads();
+    pdl_sync();
     long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= (long)B * HW) return;
     int b = (int)(pix / HW); int r = (int)(pix - (long)b * HW);
@@ -430,10 +440,10 @@ int conv_gemm(const ConvProblem& p, cudaStream_t st) {
     }
     if (p.N <= 32) {
         dim3 grid(cdiv(M, 128), cdiv(p.N, 32));
-        conv_gemm_kernel<128, 32><<<grid, NT, 0, st>>>(p, M);
+        SMK_LAUNCH((conv_gemm_kernel<128, 32>), dim3(grid), dim3(NT), 0, st, p, M);
     } else {
         dim3 grid(cdiv(M, 64), cdiv(p.N, 64));
-        conv_gemm_kernel<64, 64><<<grid, NT, 0, st>>>(p, M);
+        SMK_LAUNCH((conv_gemm_kernel<64, 64>), dim3(grid), dim3(NT), 0, st, p, M);
     }
     SMK_CHECK_LAUNCH();
     return 0;
@@ -455,9 +465,9 @@ int dwconv3x3(const float* in, int B, int H, int W, int C, int stride, const flo
     int blocks = (int)std::min<long>((total + 255) / 256, 148L * 32);
     SMK_TAG(g_prof_detail ? prof_shape_tag("dwconv3x3", (long)B * Ho * Wo, stride, C) : "dwconv3x3", 4.0 * ((double)B * H * W * C + (double)B * Ho * Wo * C + 11.0 * C), 18.0 * B * Ho * Wo * C, st);
     if (stride == 1)
-        dwconv3x3_px4_kernel<1><<<blocks, 256, 0, st>>>(in, B, H, W, C, same_pad_begin(H, 1), Ho, Wo, w9c, scale, bias, out, round_out ? 1 : 0);
+        SMK_LAUNCH((dwconv3x3_px4_kernel<1>), dim3(blocks), dim3(256), 0, st, in, B, H, W, C, same_pad_begin(H, 1), Ho, Wo, w9c, scale, bias, out, round_out ? 1 : 0);
     else
-        dwconv3x3_px4_kernel<2><<<blocks, 256, 0, st>>>(in, B, H, W, C, same_pad_begin(H, 2), Ho, Wo, w9c, scale, bias, out, round_out ? 1 : 0);
+        SMK_LAUNCH((dwconv3x3_px4_kernel<2>), dim3(blocks), dim3(256), 0, st, in, B, H, W, C, same_pad_begin(H, 2), Ho, Wo, w9c, scale, bias, out, round_out ? 1 : 0);
     SMK_CHECK_LAUNCH();
     return 0;
 }
@@ -466,7 +476,7 @@ int stem_conv(const float* img, int B, int H, int W, const float* w, const float
               cudaStream_t st) {
     int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
     SMK_TAG("stem_conv", 4.0 * ((double)B * 3 * H * W + (double)B * Ho * Wo * 16 + 27 * 16 + 32), 2.0 * 27 * 16 * (double)B * Ho * Wo, st);
-    stem_conv_kernel<<<cdiv((long)B * Ho * Wo, 128), 128, 0, st>>>(img, B, H, W, Ho, Wo, same_pad_begin(H, 2), w, scale, bias, out);
+    SMK_LAUNCH(stem_conv_kernel, dim3(cdiv((long)B * Ho * Wo, 128)), dim3(128), 0, st, img, B, H, W, Ho, Wo, same_pad_begin(H, 2), w, scale, bias, out);
     SMK_CHECK_LAUNCH();
     return 0;
 }
@@ -478,7 +488,7 @@ int stem_conv3(const float* img, int B, int H, int W, const float* const w[3], c
     for (int g = 0; g < 3; ++g) { p.w[g] = w[g]; p.scale[g] = scale[g]; p.bias[g] = bias[g]; p.out[g] = out[g]; }
     SMK_TAG("stem_conv3", 4.0 * ((double)B * 3 * H * W + (double)B * Ho * Wo * 48 + 27 * 48 + 96), 2.0 * 27 * 48 * (double)B * Ho * Wo, st);
     SMK_REQUIRE(W % 4 == 0 && W + 8 <= STEM_MAXW && same_pad_begin(H, 2) <= 1, "stem_conv3: unsupported image width %d", W);
-    stem_conv3_kernel<<<B * Ho, 128, 0, st>>>(img, B, H, W, Ho, Wo, same_pad_begin(H, 2), p);
+    SMK_LAUNCH(stem_conv3_kernel, dim3(B * Ho), dim3(128), 0, st, img, B, H, W, Ho, Wo, same_pad_begin(H, 2), p);
     SMK_CHECK_LAUNCH();
     return 0;
 }
@@ -487,14 +497,14 @@ int maxpool2x2(const float* in, int ld_in, int B, int H, int W, int C, float* ou
     long total = (long)B * (H / 2) * (W / 2) * (C / 4);
     int blocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
     SMK_TAG("maxpool2x2", 4.0 * 1.25 * (double)B * H * W * C, 0.0, st);
-    maxpool2x2_kernel<<<blocks, 256, 0, st>>>(in, ld_in, B, H, W, C, out);
+    SMK_LAUNCH(maxpool2x2_kernel, dim3(blocks), dim3(256), 0, st, in, ld_in, B, H, W, C, out);
     SMK_CHECK_LAUNCH();
     return 0;
 }
 
 int nchw_to_nhwc_pad(const float* in, int B, int C, int H, int W, int Cp, float* out, cudaStream_t st) {
     SMK_TAG("nchw_to_nhwc", 4.0 * (double)B * H * W * (C + Cp), 0.0, st);
-    nchw_to_nhwc_pad_kernel<<<cdiv((long)B * H * W, 256), 256, 0, st>>>(in, B, C, H * W, Cp, out);
+    SMK_LAUNCH(nchw_to_nhwc_pad_kernel, dim3(cdiv((long)B * H * W, 256)), dim3(256), 0, st, in, B, C, H * W, Cp, out);
     SMK_CHECK_LAUNCH();
     return 0;
 }
@@ -504,7 +514,7 @@ int conv1x1_sigmoid_nchw(const float* in, int B, int HW, int Cin, const float* w
     SMK_REQUIRE(Cout <= 4 && Cin % 4 == 0, "conv1x1_sigmoid_nchw: Cout <= 4 and Cin %% 4 == 0 required");
     size_t smem = (size_t)(Cin * Cout + Cout) * 4;
     SMK_TAG("conv1x1_sigmoid", 4.0 * (double)B * HW * (Cin + Cout), 2.0 * (double)B * HW * Cin * Cout, st);
-    conv1x1_sigmoid_kernel<<<cdiv((long)B * HW, 256), 256, smem, st>>>(in, B, HW, Cin, w, bias, Cout, out);
+    SMK_LAUNCH(conv1x1_sigmoid_kernel, dim3(cdiv((long)B * HW, 256)), dim3(256), smem, st, in, B, HW, Cin, w, bias, Cout, out);
     SMK_CHECK_LAUNCH();
     return 0;
 }
@@ -512,10 +522,10 @@ int conv1x1_sigmoid_nchw(const float* in, int B, int HW, int Cin, const float* w
 int gap_linear(const float* feat, int B, int HW, int C, const float* w, const float* bias, int n_out, const uint8_t* codes,
                float* pooled_scratch, float* out, cudaStream_t st) {
     SMK_TAG("gap_pool", 4.0 * ((double)B * HW * C + (double)B * C), (double)B * C * HW, st);
-    gap_kernel<<<dim3(B, cdiv(C, 64)), 256, 0, st>>>(feat, HW, C, pooled_scratch);
+    SMK_LAUNCH(gap_kernel, dim3(dim3(B, cdiv(C, 64))), dim3(256), 0, st, feat, HW, C, pooled_scratch);
     SMK_CHECK_LAUNCH();
     SMK_TAG("head_linear", 4.0 * ((double)B * C + (double)n_out * C + (double)B * n_out), 2.0 * (double)B * C * n_out, st);
-    head_linear_kernel<<<dim3(B, cdiv(n_out, 8)), 256, 0, st>>>(pooled_scratch, C, w, bias, n_out, codes, out);
+    SMK_LAUNCH(head_linear_kernel, dim3(dim3(B, cdiv(n_out, 8))), dim3(256), 0, st, pooled_scratch, C, w, bias, n_out, codes, out);
     SMK_CHECK_LAUNCH();
     return 0;
 }

@@ -43,6 +43,7 @@ __device__ __forceinline__ float pix_to_ndc(int i, int S) {
 __global__ void __launch_bounds__(256)
 project_kernel(const float* __restrict__ pts, const float* __restrict__ cam, int B, int L, int out_dim,
                float* __restrict__ out) {
+    smk::pdl_sync();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)B * L) return;
     int b = (int)(i / L);
@@ -59,6 +60,7 @@ project_kernel(const float* __restrict__ pts, const float* __restrict__ cam, int
 __global__ void __launch_bounds__(128)
 submesh_kernel(RenderDev d, const float* __restrict__ verts, const float* __restrict__ tverts, int B,
                float* __restrict__ rv /*[B][NM][3]*/, float* __restrict__ normals /*[B][NM][3]*/) {
+    smk::pdl_sync();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int b = blockIdx.y;
     if (i >= d.NM) return;
@@ -90,6 +92,7 @@ submesh_kernel(RenderDev d, const float* __restrict__ verts, const float* __rest
 __global__ void __launch_bounds__(128)
 tri_setup_kernel(RenderDev d, const float* __restrict__ rv, int B, float* __restrict__ recs /*[B][F][REC]*/,
                  uint32_t* __restrict__ ranges /*[B][F]*/) {
+    smk::pdl_sync();
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     int b = blockIdx.y;
     if (f >= d.F) return;
@@ -141,6 +144,7 @@ raster_tile_kernel(RenderDev d, const float* __restrict__ recs, const uint32_t* 
     const uint32_t tx = blockIdx.x, ty = blockIdx.y;
     if (tid == 0) s_count = 0;
     __syncthreads();
+    smk::pdl_sync();
     // -- bin: compact the ids of triangles whose conservative tile range covers this tile
     //    (4 packed ranges per thread per pass: one 16-byte load, one shared atomic per warp)
     const uint4* rg4 = reinterpret_cast<const uint4*>(ranges + (size_t)b * d.F);
@@ -317,7 +321,7 @@ extern "C" int smk_project_points(const float* pts, const float* cam, int B, int
     SMK_REQUIRE(pts && cam && out_xy, "smk_project_points: null argument");
     if (B <= 0 || L <= 0) return 0;
     SMK_TAG("project_points", 4.0 * B * (5.0 * L + 3), 4.0 * B * L, (cudaStream_t)stream);
-    project_kernel<<<smk::cdiv((long)B * L, 256), 256, 0, (cudaStream_t)stream>>>(pts, cam, B, L, 2, out_xy);
+    SMK_LAUNCH(project_kernel, dim3(smk::cdiv((long)B * L, 256)), dim3(256), 0, (cudaStream_t)stream, pts, cam, B, L, 2, out_xy);
     SMK_CHECK_LAUNCH();
     return 0;
 }
@@ -338,18 +342,18 @@ extern "C" int smk_renderer_forward(const SmkRenderer* h, const float* verts, co
     uint32_t* ranges = w.take<uint32_t>((size_t)B * d.F);
     float* nrm = normals_out ? normals_out : nrm_ws;
     SMK_TAG("project_verts", 4.0 * B * (6.0 * d.V + 3), 5.0 * B * d.V, st);
-    project_kernel<<<smk::cdiv((long)B * d.V, 256), 256, 0, st>>>(verts, cam, B, d.V, 3, tverts);
+    SMK_LAUNCH(project_kernel, dim3(smk::cdiv((long)B * d.V, 256)), dim3(256), 0, st, verts, cam, B, d.V, 3, tverts);
     SMK_CHECK_LAUNCH();
     SMK_TAG("submesh_normals", 4.0 * B * (9.0 * d.NM) + 4.0 * (4.0 * d.F + 2.0 * d.NM), 30.0 * B * 3.0 * d.F, st);
-    submesh_kernel<<<dim3(smk::cdiv(d.NM, 128), B), 128, 0, st>>>(d, verts, tverts, B, rv, nrm);
+    SMK_LAUNCH(submesh_kernel, dim3(dim3(smk::cdiv(d.NM, 128), B)), dim3(128), 0, st, d, verts, tverts, B, rv, nrm);
     SMK_CHECK_LAUNCH();
     SMK_TAG("tri_setup", 4.0 * B * (3.0 * d.NM + (double)d.F * (REC + 1)) + 12.0 * d.F, 40.0 * B * d.F, st);
-    tri_setup_kernel<<<dim3(smk::cdiv(d.F, 128), B), 128, 0, st>>>(d, rv, B, recs, ranges);
+    SMK_LAUNCH(tri_setup_kernel, dim3(dim3(smk::cdiv(d.F, 128), B)), dim3(128), 0, st, d, rv, B, recs, ranges);
     SMK_CHECK_LAUNCH();
     size_t smem = (size_t)CHUNK * REC * 4 + (((size_t)d.F * 2 + 15) & ~size_t(15));
     dim3 grid(d.S / TILE_W, d.S / TILE_H, B);
     SMK_TAG("raster_tile", 4.0 * B * ((double)d.F * (REC + 1) + 3.0 * d.NM + (double)d.S * d.S * (3 + (pix_to_face ? 2 : 0) + (bary ? 3 : 0) + (zbuf ? 1 : 0))), 0.0, st);
-    raster_tile_kernel<<<grid, dim3(TILE_W, TILE_H), smem, st>>>(d, recs, ranges, nrm, h->lights, B, rendered, pix_to_face, bary, zbuf);
+    SMK_LAUNCH(raster_tile_kernel, dim3(grid), dim3(dim3(TILE_W, TILE_H)), smem, st, d, recs, ranges, nrm, h->lights, B, rendered, pix_to_face, bary, zbuf);
     SMK_CHECK_LAUNCH();
     return 0;
 }

@@ -34,6 +34,8 @@ constexpr int STAGE_BYTES = 2 * HALF_BYTES + B_BYTES;   // 36 KiB
 constexpr int STAGES = 2;
 constexpr int E_PITCH = NC + 4;                 // floats; 144-byte rows (odd multiple of 16 B): conflict-free 16-byte column writes
 constexpr int E_BYTES = 256 * E_PITCH * 4;      // 36 864 B
+constexpr int PAR_ROWS = 13;                     // scale1, bias1, 9 depthwise taps, scale2, bias2
+constexpr int PAR_BYTES = 2 * PAR_ROWS * NC * 4;  // double-buffered: 3328 B
 constexpr int NUM_WORKERS = 256;
 constexpr int NUM_THREADS = 64 + NUM_WORKERS;
 constexpr uint32_t TMEM_COLS = 128;             // (2 buffers) x (2 halves) x 32 columns
@@ -133,7 +135,8 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     // the shared address space visible to the compiler, so E is accessed with LDS/STS instead of generic LD/ST.
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* E = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + E_BYTES);
+    float* PAR = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + E_BYTES);        // [2][PAR_ROWS][NC]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + E_BYTES + PAR_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* acc_full = empty + STAGES;
     uint64_t* acc_empty = acc_full + 2;
@@ -170,6 +173,7 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -225,74 +229,131 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         const int half = wid >> 2;                         // warps {2..5} drain the upper 16x8 pixels, {6..9} the lower
         const int t = threadIdx.x - 64;                    // 0..255
         const int cq = t & 7, slot = t >> 3;               // depthwise role: channel quad within the chunk, output slot (0..31)
+        // Per-chunk parameters (BN1 scale/bias, nine depthwise taps, BN2 scale/bias: 13 rows of 32 channels) are
+        // staged through a double-buffered shared-memory block: thread t < 208 owns one float2 of the block, loads
+        // it for chunk i+1 before it starts waiting for the accumulator of chunk i and parks it after phase (a) —
+        // the global-load latency is off the critical path and phases (a)/(b) read parameters with LDS.
+        const int prow = t >> 4, pcol = (t & 15) * 2;
+        const float* psrc = nullptr;
+        if (t < PAR_ROWS * 16) {
+            psrc = prow == 0 ? a.scale1 : prow == 1 ? a.bias1 : prow == 11 ? a.scale2 : prow == 12 ? a.bias2 : a.wdw + (size_t)(prow - 2) * a.mid;
+            psrc += pcol;
+        }
+        auto load_par = [&](int c) {
+            float2 v = make_float2(0.f, 0.f);
+            if (psrc && c * NC + pcol < a.mid) v = __ldg(reinterpret_cast<const float2*>(psrc + c * NC));
+            return v;
+        };
+        auto park_par = [&](int slot_idx, const float2& v) {
+            if (psrc) *reinterpret_cast<float2*>(PAR + slot_idx * (PAR_ROWS * NC) + prow * NC + pcol) = v;
+        };
+        if ((int)blockIdx.x < a.n_items) park_par(0, load_par(decode(blockIdx.x).c_begin));
+        worker_barrier();
         int cc = 0;
         for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
           const Item w = decode(item);
           const int img = w.img, oh0 = w.oh0, ow0 = w.ow0;
           const int ey0 = oh0 * STRIDE - a.pad, ex0 = ow0 * STRIDE - a.pad;
+          // depthwise role of this thread for the tile: output column dw_ox, output rows [dw_oy0, dw_oy1)
+          // (the valid columns x as many row groups as fit in the 32 slots)
+          const int ncols = min(TO, a.Wo - ow0), nrows = min(TO, a.Ho - oh0);
+          const int n_rg = min(32 / ncols, nrows), rpt = (nrows + n_rg - 1) / n_rg;
+          const int dw_ox = slot % ncols, dw_rg = slot / ncols;
+          const int dw_oy0 = dw_rg * rpt, dw_oy1 = dw_rg < n_rg ? min(nrows, dw_oy0 + rpt) : 0;
+          int next_first = -1;                             // first chunk of this CTA's next item (-1: none)
+          if (item + (int)gridDim.x < a.n_items) next_first = decode(item + gridDim.x).c_begin;
           for (int c = w.c_begin; c < w.c_end; ++c, ++cc) {
             const int buf = cc & 1;
             const int ch0 = c * NC;
-            const int nvalid = min(NC, a.mid - ch0);       // channels of this chunk that exist
-            const bool dw_active = cq * 4 < nvalid;
-            const int chd = ch0 + (dw_active ? cq * 4 : 0);
+            const float* par = PAR + buf * (PAR_ROWS * NC);
+            const int c_next = c + 1 < w.c_end ? c + 1 : next_first;
+            float2 pf = make_float2(0.f, 0.f);
+            if (c_next >= 0) pf = load_par(c_next);
             mbar_wait(&acc_full[buf], (uint32_t)(cc >> 1) & 1u);
             tcgen05_fence_after();
-            // (a) TMEM -> BN1 + ReLU -> E   (rows = window pixels, lane = pixel)
+            // (a) TMEM -> BN1 + ReLU -> E   (rows = window pixels, lane = pixel).  Channels past `mid` have zero
+            // scale and bias in the parameter block, pixels outside the image are zeroed: that is the zero
+            // padding of e the depthwise conv expects.
             {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * 2 + half) * NC), v);
+                float4 v[8];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * 2 + half) * NC), reinterpret_cast<float*>(v));
                 const int r = quarter * 32 + lane;                       // row within the half: r = hh*16 + ww
                 const int ey = ey0 + half * 8 + (r >> 4), ex = ex0 + (r & 15);
                 const bool inside = ey >= 0 && ey < a.H && ex >= 0 && ex < a.W;
                 float* erow = E + (size_t)(half * 128 + r) * E_PITCH;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (inside && j < nvalid) {
-                        const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale1 + ch0 + j));
-                        const float4 bi = __ldg(reinterpret_cast<const float4*>(a.bias1 + ch0 + j));
-                        o.x = fmaxf(fmaf(v[j], sc.x, bi.x), 0.f); o.y = fmaxf(fmaf(v[j + 1], sc.y, bi.y), 0.f);
-                        o.z = fmaxf(fmaf(v[j + 2], sc.z, bi.z), 0.f); o.w = fmaxf(fmaf(v[j + 3], sc.w, bi.w), 0.f);
-                    }
-                    *reinterpret_cast<float4*>(erow + j) = o;
+                for (int j = 0; j < 8; ++j) {
+                    const float4 sc = *reinterpret_cast<const float4*>(par + 4 * j);
+                    const float4 bi = *reinterpret_cast<const float4*>(par + NC + 4 * j);
+                    float4 o = fma4(v[j], sc, bi);
+                    o.x = inside ? fmaxf(o.x, 0.f) : 0.f; o.y = inside ? fmaxf(o.y, 0.f) : 0.f;
+                    o.z = inside ? fmaxf(o.z, 0.f) : 0.f; o.w = inside ? fmaxf(o.w, 0.f) : 0.f;
+                    *reinterpret_cast<float4*>(erow + 4 * j) = o;
                 }
             }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);   // this warp has drained its part of the accumulator
+            if (c_next >= 0) park_par(buf ^ 1, pf);        // slot buf^1 was last read in the previous chunk's phase (b)
             worker_barrier();
-            // (b) depthwise 3x3 over E: thread = (channel quad, output slot), outputs slot, slot+16, ...
-            if (dw_active) {
-                const int ch = chd;
-                float4 k[9];                                // (hoisting these above the accumulator wait costs spills: measured slower)
+            // (b) depthwise 3x3 over E.  One thread owns one output column of one channel quad and walks down
+            // its rows, so every E row it reads is shared by the (up to three) output rows it feeds: 3 LDS.128
+            // per input row instead of 9 per output.  Tap order per output stays (ky, kx) ascending -> same
+            // rounding as the unfused path.
+            if (cq * 4 < a.mid - ch0 && dw_oy0 < dw_oy1) {
+                const int ch = ch0 + cq * 4;
+                float4 k[9];
 #pragma unroll
-                for (int q = 0; q < 9; ++q) k[q] = __ldg(reinterpret_cast<const float4*>(a.wdw + (size_t)q * a.mid + ch));
-                const float4 s2 = __ldg(reinterpret_cast<const float4*>(a.scale2 + ch));
-                const float4 b2 = __ldg(reinterpret_cast<const float4*>(a.bias2 + ch));
-                for (int p = slot; p < TO * TO; p += 32) {
-                    const int oy = p / TO, ox = p - oy * TO;
-                    const int oh = oh0 + oy, ow = ow0 + ox;
-                    if (oh >= a.Ho || ow >= a.Wo) continue;
-                    const float* e0 = E + (size_t)((oy * STRIDE) * WIN + ox * STRIDE) * E_PITCH + cq * 4;
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const float4 x = *reinterpret_cast<const float4*>(e0 + (size_t)(ky * WIN + kx) * E_PITCH);
-                            const float4 kk = k[ky * 3 + kx];
-                            acc.x = fmaf(x.x, kk.x, acc.x); acc.y = fmaf(x.y, kk.y, acc.y);
-                            acc.z = fmaf(x.z, kk.z, acc.z); acc.w = fmaf(x.w, kk.w, acc.w);
-                        }
-                    float4 o;
-                    o.x = fmaxf(fmaf(acc.x, s2.x, b2.x), 0.f); o.y = fmaxf(fmaf(acc.y, s2.y, b2.y), 0.f);
-                    o.z = fmaxf(fmaf(acc.z, s2.z, b2.z), 0.f); o.w = fmaxf(fmaf(acc.w, s2.w, b2.w), 0.f);
+                for (int q = 0; q < 9; ++q) k[q] = *reinterpret_cast<const float4*>(par + (2 + q) * NC + cq * 4);
+                const float4 s2 = *reinterpret_cast<const float4*>(par + 11 * NC + cq * 4);
+                const float4 b2 = *reinterpret_cast<const float4*>(par + 12 * NC + cq * 4);
+                float* orow = a.out + (((size_t)img * a.Ho + oh0 + dw_oy0) * a.Wo + ow0 + dw_ox) * a.mid + ch;
+                const size_t orow_stride = (size_t)a.Wo * a.mid;
+                auto emit = [&](const float4& acc) {
+                    float4 o = fma4(acc, s2, b2);
+                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                     if (a.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-                    *reinterpret_cast<float4*>(a.out + (((size_t)img * a.Ho + oh) * a.Wo + ow) * a.mid + ch) = o;
+                    *reinterpret_cast<float4*>(orow) = o;
+                    orow += orow_stride;
+                };
+                const float* e = E + (size_t)((dw_oy0 * STRIDE) * WIN + dw_ox * STRIDE) * E_PITCH + cq * 4;
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (STRIDE == 1) {
+                    float4 acc0 = zero, acc1 = zero, acc2 = zero;          // outputs r-2 (gets ky=2), r-1 (ky=1), r (ky=0)
+                    const int n_in = dw_oy1 - dw_oy0 + 2;
+#pragma unroll 3
+                    for (int r = 0; r < n_in; ++r, e += WIN * E_PITCH) {
+                        const float4 x0 = *reinterpret_cast<const float4*>(e);
+                        const float4 x1 = *reinterpret_cast<const float4*>(e + E_PITCH);
+                        const float4 x2 = *reinterpret_cast<const float4*>(e + 2 * E_PITCH);
+                        fma4_acc(acc0, x0, k[6]); fma4_acc(acc0, x1, k[7]); fma4_acc(acc0, x2, k[8]);
+                        fma4_acc(acc1, x0, k[3]); fma4_acc(acc1, x1, k[4]); fma4_acc(acc1, x2, k[5]);
+                        fma4_acc(acc2, x0, k[0]); fma4_acc(acc2, x1, k[1]); fma4_acc(acc2, x2, k[2]);
+                        if (r >= 2) emit(acc0);
+                        acc0 = acc1; acc1 = acc2; acc2 = zero;
+                    }
+                } else {
+                    float4 p0 = *reinterpret_cast<const float4*>(e);
+                    float4 p1 = *reinterpret_cast<const float4*>(e + E_PITCH);
+                    float4 p2 = *reinterpret_cast<const float4*>(e + 2 * E_PITCH);
+                    for (int oy = dw_oy0; oy < dw_oy1; ++oy) {
+                        e += WIN * E_PITCH;
+                        float4 acc = zero;
+                        fma4_acc(acc, p0, k[0]); fma4_acc(acc, p1, k[1]); fma4_acc(acc, p2, k[2]);
+                        const float4 m0 = *reinterpret_cast<const float4*>(e);
+                        const float4 m1 = *reinterpret_cast<const float4*>(e + E_PITCH);
+                        const float4 m2 = *reinterpret_cast<const float4*>(e + 2 * E_PITCH);
+                        fma4_acc(acc, m0, k[3]); fma4_acc(acc, m1, k[4]); fma4_acc(acc, m2, k[5]);
+                        e += WIN * E_PITCH;
+                        p0 = *reinterpret_cast<const float4*>(e);
+                        p1 = *reinterpret_cast<const float4*>(e + E_PITCH);
+                        p2 = *reinterpret_cast<const float4*>(e + 2 * E_PITCH);
+                        fma4_acc(acc, p0, k[6]); fma4_acc(acc, p1, k[7]); fma4_acc(acc, p2, k[8]);
+                        emit(acc);
+                    }
                 }
             }
-            worker_barrier();                              // E is free for the next chunk
+            worker_barrier();                              // E and the parameter slot are free for the next chunk
           }
         }
     }
@@ -357,7 +418,8 @@ int xdw_conv(const XdwConv& p, cudaStream_t st) {
     a.pad = p.stride == 1 ? 1 : 0;
     a.tiles_x = cdiv(Wo, TO); a.tiles_y = cdiv(Ho, TO);
     a.scale1 = p.scale1; a.bias1 = p.bias1; a.wdw = p.wdw; a.scale2 = p.scale2; a.bias2 = p.bias2; a.out = p.out; a.round_out = p.round_out;
-    constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + E_BYTES + 1024 + 256;
+    constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + E_BYTES + PAR_BYTES + 1024 + 256;
+    static_assert(2 * (smem + 1024) <= 228 * 1024, "two CTAs per SM");
     static unsigned long long configured_mask = 0;       // per-device attribute, see gemm_tc.cu
     int dev = 0;
     SMK_CHECK_CUDA(cudaGetDevice(&dev));
@@ -374,8 +436,8 @@ int xdw_conv(const XdwConv& p, cudaStream_t st) {
     }
     a.n_items = a.tiles_x * a.tiles_y * p.B * a.groups;
     dim3 grid((unsigned)std::min(a.n_items, 2 * 148));          // persistent: 2 CTAs per SM
-    if (p.stride == 1) xdw_kernel<1><<<grid, NUM_THREADS, smem, st>>>(tmX, tmW, a);
-    else xdw_kernel<2><<<grid, NUM_THREADS, smem, st>>>(tmX, tmW, a);
+    if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1>), dim3(grid), dim3(NUM_THREADS), smem, st, tmX, tmW, a);
+    else SMK_LAUNCH((xdw_kernel<2>), dim3(grid), dim3(NUM_THREADS), smem, st, tmX, tmW, a);
     SMK_CHECK_LAUNCH();
     return 0;
 }
