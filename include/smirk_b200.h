@@ -182,6 +182,13 @@ int smk_debug_xdw(const float* x, int B, int H, int W, int Cin, const float* w1t
                   int mid, const float* wdw, const float* scale2, const float* bias2, int stride, int round_out,
                   float* out, void* stream);
 
+/*   smk_debug_stem_ds: fused stem conv (3x3 s2, 3 -> 16) + BN + ReLU + depthwise-separable block 0 (fp32 CUDA cores).
+ *                      img [B,3,H,W] NCHW; stem_w [27][16] (k = (c*3+ky)*3+kx); dw_w [9][16]; pw_w [16 ci][16 co];
+ *                      out [B,H/2/stride,W/2/stride,16] NHWC; the skip connection is added when stride == 1.          */
+int smk_debug_stem_ds(const float* img, int B, int H, int W, const float* stem_w, const float* stem_s, const float* stem_b,
+                      const float* dw_w, const float* dw_s, const float* dw_b, const float* pw_w, const float* pw_s,
+                      const float* pw_b, int stride, int round_out, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

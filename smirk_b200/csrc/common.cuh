@@ -117,6 +117,14 @@ __device__ __forceinline__ void fma4_acc(float4& acc, const float4& x, const flo
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a[0]) : "l"(xx[0]), "l"(kk[0]));
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a[1]) : "l"(xx[1]), "l"(kk[1]));
 }
+__device__ __forceinline__ void fma4_s(float4& acc, float x, const float4& k) {              // acc += x * k (scalar x)
+    uint64_t xx;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x));
+    uint64_t* a = reinterpret_cast<uint64_t*>(&acc);
+    const uint64_t* kk = reinterpret_cast<const uint64_t*>(&k);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a[0]) : "l"(xx), "l"(kk[0]));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a[1]) : "l"(xx), "l"(kk[1]));
+}
 __device__ __forceinline__ float4 fma4(const float4& x, const float4& s, const float4& b) {  // x * s + b
     float4 o;
     uint64_t* oo = reinterpret_cast<uint64_t*>(&o);

@@ -9,6 +9,7 @@
 #include "gemm_tc.cuh"
 #include "xdw_tc.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -19,7 +20,7 @@ constexpr float kBnEps = 1e-3f;
 struct ConvW { float* w = nullptr; float* wt = nullptr; float* scale = nullptr; float* bias = nullptr; int cin = 0, cout = 0; };   // w: [K][N] fp32 path, wt: [N][K] tcgen05 path
 enum Kind { DS = 0, IR = 1, CN = 2 };
 struct BlockDef { Kind kind; int stride; float exp; int cout; };
-struct Block { Kind kind; int stride, cin, mid, cout; bool skip; ConvW pw, dw, pwl; };
+struct Block { Kind kind; int stride, cin, mid, cout; bool skip; ConvW pw, dw, pwl; ConvW pw_f32; };   // pw_f32: fp32 [K][N] copy of a DS block's 1x1 (fused stem path)
 
 struct Backbone {
     ConvW stem;
@@ -129,7 +130,9 @@ extern "C" int smk_encoder_create(const SmkEncoderDesc* desc, SmkEncoder** out) 
             b.skip = b.kind != CN && b.stride == 1 && b.cin == b.cout;
             if (b.kind == DS) {
                 b.mid = cin;
-                ok = fold_conv(cur, 1, cin, cin, false, h->arena, &b.dw, &e) && fold_conv(cur, 0, cin, b.cout, tc, h->arena, &b.pw, &e);
+                ok = fold_conv(cur, 1, cin, cin, false, h->arena, &b.dw, &e);
+                if (ok && tc) { TensorCursor again = cur; ok = fold_conv(again, 0, cin, b.cout, false, h->arena, &b.pw_f32, &e); }
+                ok = ok && fold_conv(cur, 0, cin, b.cout, tc, h->arena, &b.pw, &e);
             } else if (b.kind == IR) {
                 b.mid = make_divisible((double)cin * defs[k].exp);
                 ok = fold_conv(cur, 0, cin, b.mid, tc, h->arena, &b.pw, &e) && fold_conv(cur, 1, b.mid, b.mid, false, h->arena, &b.dw, &e) &&
@@ -210,7 +213,11 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
     // overlap; join before returning.  Event record/wait on other streams is legal under stream capture,
     // so a CUDA graph of the caller's stream gets three parallel branches.
     const bool concurrent = !smk::profiling();   // the event profiler wants one kernel at a time
-    {   // all three stems in one pass over the image (it is the only tensor the backbones share)
+    // precision 2: stem + block 0 (depthwise-separable, 16 channels at 112 x 112) run as one kernel per backbone —
+    // the three largest activations never reach HBM.
+    static const int fuse_stem_env = []() { const char* e = getenv("SMK_FUSE_STEM"); return e ? atoi(e) : 1; }();
+    const bool fuse_stem = h->fuse_xdw && fuse_stem_env && h->bb[0].blocks[0].kind == DS && h->bb[0].blocks[0].pw_f32.w;
+    if (!fuse_stem) {   // all three stems in one pass over the image (it is the only tensor the backbones share)
         const float* sw[3]; const float* ss[3]; const float* sb[3]; float* so[3];
         for (int i = 0; i < 3; ++i) { sw[i] = h->bb[i].stem.w; ss[i] = h->bb[i].stem.scale; sb[i] = h->bb[i].stem.bias; so[i] = bufs[i][0]; }
         if (int rc = smk::stem_conv3(img, B, 224, 224, sw, ss, sb, so, main_st)) return rc;
@@ -226,7 +233,15 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
         float* const* buf = bufs[i];
         float *x = buf[0], *y = buf[1], *e = buf[2], *d = buf[3];
         int res = 112;
-        for (const Block& b : bb.blocks) {
+        size_t first = 0;
+        if (fuse_stem) {
+            const Block& b0 = bb.blocks[0];
+            rc = smk::stem_ds(img, B, 224, 224, bb.stem.w, bb.stem.scale, bb.stem.bias, b0.dw.w, b0.dw.scale, b0.dw.bias,
+                              b0.pw_f32.w, b0.pw_f32.scale, b0.pw_f32.bias, b0.stride, 1, x, st);
+            res = 112 / b0.stride; first = 1;
+        }
+        for (size_t bi = first; bi < bb.blocks.size() && !rc; ++bi) {
+            const Block& b = bb.blocks[bi];
             int ro = (res + b.stride - 1) / b.stride;
             if (b.kind == DS) {
                 rc = smk::dwconv3x3(x, B, res, res, b.cin, b.stride, b.dw.w, b.dw.scale, b.dw.bias, d, st, h->precision == 1);

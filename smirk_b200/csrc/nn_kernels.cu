@@ -493,6 +493,179 @@ int stem_conv3(const float* img, int B, int H, int W, const float* const w[3], c
     return 0;
 }
 
+// ---- fused stem + first block --------------------------------------------------------------------------
+// conv_stem 3x3 s2 (3 -> 16) + BN + ReLU  ->  block 0 of tf_mobilenetv3_*_minimal_100, a depthwise-separable
+// block (depthwise 3x3 s{1,2} + BN + ReLU -> 1x1 16 -> 16 + BN, + skip when stride 1); reference
+// src/smirk_encoder.py:7-12 -> timm MobileNetV3.conv_stem/bn1 + DepthwiseSeparableConv.  These are the three
+// largest activations of a backbone (112 x 112 x 16); unfused they cost a 96 MB stem pass plus a depthwise and
+// a 1x1 kernel per backbone.  Here a CTA owns a 16 x 16 tile of the stem output (+1 halo = 18 x 18):
+//   1. stage the 37 x 37 x 3 image patch in shared memory, even/odd columns de-interleaved so the stride-2 taps
+//      of neighbouring pixels hit neighbouring banks;
+//   2. stem conv: thread = two stem pixels x 16 channels (the tap weights, broadcast from shared memory, are
+//      used twice), BN + ReLU, zero outside the 112 x 112 map (= the depthwise conv's zero padding) -> S;
+//   3. depthwise 3x3 over S: thread = (pixel, channel quad), taps in registers, BN + ReLU -> D (aliases the patch);
+//   4. 1x1 conv on D: thread = (pixel, output-channel quad), 16 x 4 weights in registers, BN, + S (skip),
+//      optional TF32 rounding, one coalesced 16-byte store per thread.
+// All arithmetic is fp32 FMA in the reference's tap order; the image is the only HBM read, the block output the
+// only write.
+namespace {
+constexpr int SD_T = 16, SD_ST = SD_T + 2;                 // stem-resolution tile edge, with halo
+constexpr int SD_PR = 2 * SD_ST + 1;                       // image patch rows / cols (37)
+constexpr int SD_PP = 20;                                  // patch row pitch per column parity (19 even + 18 odd columns)
+struct StemDs {
+    const float* stem_w; const float* stem_s; const float* stem_b;      // [27][16], [16], [16]
+    const float* dw_w; const float* dw_s; const float* dw_b;            // [9][16]
+    const float* pw_w; const float* pw_s; const float* pw_b;            // [16 ci][16 co]
+    float* out; int round_out;
+};
+
+template <int STRIDE>
+__global__ void __launch_bounds__(256, 3)
+stem_ds_kernel(const float* __restrict__ img, int H, int W, int Hs, int Ws, int pad, StemDs p) {
+    constexpr int PADO = STRIDE == 1 ? 1 : 0;              // depthwise TF-SAME pad_begin on an even-sized map
+    constexpr int TO = SD_T / STRIDE;                      // output tile edge
+    __shared__ __align__(16) float sP[3 * SD_PR * 2 * SD_PP];          // image patch [c][row][parity][col/2]; later D [256][16]
+    __shared__ __align__(16) float sS[SD_ST * SD_ST * 16];             // stem tile [pixel][16]
+    __shared__ __align__(16) float sW[27 * 16];
+    __shared__ __align__(16) float sK[9 * 16 + 16 * 16];               // depthwise taps, 1x1 weights
+    __shared__ __align__(16) float sB[6 * 16];                         // stem / dw / pw scale, bias
+    const int tid = threadIdx.x, b = blockIdx.y;
+    const int tiles_x = Ws / SD_T;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int sy0 = ty * SD_T - PADO, sx0 = tx * SD_T - PADO;          // stem-tile origin
+    const int iy0 = 2 * sy0 - pad, ix0 = 2 * sx0 - pad;                // image-patch origin
+    for (int i = tid; i < 27 * 16; i += 256) sW[i] = p.stem_w[i];
+    for (int i = tid; i < 9 * 16; i += 256) sK[i] = p.dw_w[i];
+    sK[9 * 16 + tid] = p.pw_w[tid];
+    if (tid < 16) {
+        sB[tid] = p.stem_s[tid]; sB[16 + tid] = p.stem_b[tid]; sB[32 + tid] = p.dw_s[tid]; sB[48 + tid] = p.dw_b[tid];
+        sB[64 + tid] = p.pw_s[tid]; sB[80 + tid] = p.pw_b[tid];
+    }
+    pdl_sync();                                            // weights are constants; the image and the outputs are not
+    // ix0 and W are even: one 8-byte load fetches an (even, odd) column pair — exactly the de-interleaved layout.
+    // 19 pairs per row cover the 37 columns (the odd half of the last pair is never read).
+    constexpr int SD_PAIRS = (SD_PR + 1) / 2;
+#pragma unroll 4
+    for (int i = tid; i < 3 * SD_PR * SD_PAIRS; i += 256) {
+        const int row = i / SD_PAIRS, j = i - row * SD_PAIRS, c = row / SD_PR, r = row - c * SD_PR;
+        const int iy = iy0 + r, ix = ix0 + 2 * j;
+        float2 v = make_float2(0.f, 0.f);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float2*>(img + (((size_t)b * 3 + c) * H + iy) * W + ix));
+        sP[(row * 2) * SD_PP + j] = v.x;
+        sP[(row * 2 + 1) * SD_PP + j] = v.y;
+    }
+    __syncthreads();
+    // -- 2. stem conv: pixels (syp, sx) and (syp + 9, sx)
+    if (tid < SD_ST * SD_ST / 2) {
+        const int syp = tid / SD_ST, sx = tid - syp * SD_ST;
+        float4 a0[4], a1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a0[q] = a1[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int off = (kx & 1) * SD_PP + sx + (kx >> 1);
+                    const float x0 = sP[(c * SD_PR + 2 * syp + ky) * 2 * SD_PP + off];
+                    const float x1 = sP[(c * SD_PR + 2 * (syp + SD_ST / 2) + ky) * 2 * SD_PP + off];
+                    const float4* wk = reinterpret_cast<const float4*>(sW + ((c * 3 + ky) * 3 + kx) * 16);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { const float4 w4 = wk[q]; fma4_s(a0[q], x0, w4); fma4_s(a1[q], x1, w4); }
+                }
+        const bool in_x = sx0 + sx >= 0 && sx0 + sx < Ws;
+        const bool v0 = in_x && sy0 + syp >= 0 && sy0 + syp < Hs;
+        const bool v1 = in_x && sy0 + syp + SD_ST / 2 >= 0 && sy0 + syp + SD_ST / 2 < Hs;
+        float4* s0 = reinterpret_cast<float4*>(sS + (syp * SD_ST + sx) * 16);
+        float4* s1 = reinterpret_cast<float4*>(sS + ((syp + SD_ST / 2) * SD_ST + sx) * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 sc = *reinterpret_cast<const float4*>(sB + 4 * q), bi = *reinterpret_cast<const float4*>(sB + 16 + 4 * q);
+            float4 o0 = fma4(a0[q], sc, bi), o1 = fma4(a1[q], sc, bi);
+            o0.x = v0 ? fmaxf(o0.x, 0.f) : 0.f; o0.y = v0 ? fmaxf(o0.y, 0.f) : 0.f; o0.z = v0 ? fmaxf(o0.z, 0.f) : 0.f; o0.w = v0 ? fmaxf(o0.w, 0.f) : 0.f;
+            o1.x = v1 ? fmaxf(o1.x, 0.f) : 0.f; o1.y = v1 ? fmaxf(o1.y, 0.f) : 0.f; o1.z = v1 ? fmaxf(o1.z, 0.f) : 0.f; o1.w = v1 ? fmaxf(o1.w, 0.f) : 0.f;
+            s0[q] = o0; s1[q] = o1;
+        }
+    }
+    __syncthreads();
+    // -- 3. depthwise 3x3: thread = (pixel, channel quad)
+    float* sD = sP;
+    const int q = tid & 3;
+    {
+        float4 k[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) k[t] = *reinterpret_cast<const float4*>(sK + t * 16 + 4 * q);
+        const float4 sc = *reinterpret_cast<const float4*>(sB + 32 + 4 * q), bi = *reinterpret_cast<const float4*>(sB + 48 + 4 * q);
+#pragma unroll
+        for (int j = 0; j < TO * TO / 64; ++j) {
+            const int px = (tid >> 2) + 64 * j, oy = px / TO, ox = px - oy * TO;
+            const float* s = sS + ((oy * STRIDE) * SD_ST + ox * STRIDE) * 16 + 4 * q;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+                    fma4_acc(acc, *reinterpret_cast<const float4*>(s + (ky * SD_ST + kx) * 16), k[ky * 3 + kx]);
+            float4 o = fma4(acc, sc, bi);
+            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            *reinterpret_cast<float4*>(sD + px * 16 + 4 * q) = o;
+        }
+    }
+    __syncthreads();
+    // -- 4. 1x1 conv: thread = (pixel, output-channel quad)
+    {
+        constexpr int NJ = TO * TO / 64;                   // pixels per thread
+        const float4 sc = *reinterpret_cast<const float4*>(sB + 64 + 4 * q), bi = *reinterpret_cast<const float4*>(sB + 80 + 4 * q);
+        const int Ho = Hs / STRIDE, Wo = Ws / STRIDE;
+        float4 accs[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) accs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {                      // four input channels at a time: their weights serve all NJ pixels
+            float4 w[4];
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) w[ci] = *reinterpret_cast<const float4*>(sK + 9 * 16 + (4 * g + ci) * 16 + 4 * q);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const float4 d = *reinterpret_cast<const float4*>(sD + ((tid >> 2) + 64 * j) * 16 + 4 * g);
+                fma4_s(accs[j], d.x, w[0]); fma4_s(accs[j], d.y, w[1]); fma4_s(accs[j], d.z, w[2]); fma4_s(accs[j], d.w, w[3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int px = (tid >> 2) + 64 * j, oy = px / TO, ox = px - oy * TO;
+            float4 o = fma4(accs[j], sc, bi);
+            if (STRIDE == 1) {                             // skip connection: block input = stem output at the same pixel
+                const float4 r = *reinterpret_cast<const float4*>(sS + ((oy + 1) * SD_ST + ox + 1) * 16 + 4 * q);
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            }
+            if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+            const int oh = ty * TO + oy, ow = tx * TO + ox;
+            *reinterpret_cast<float4*>(p.out + (((size_t)b * Ho + oh) * Wo + ow) * 16 + 4 * q) = o;
+        }
+    }
+}
+}  // namespace
+
+int stem_ds(const float* img, int B, int H, int W, const float* stem_w, const float* stem_s, const float* stem_b,
+            const float* dw_w, const float* dw_s, const float* dw_b, const float* pw_w, const float* pw_s, const float* pw_b,
+            int stride, int round_out, float* out, cudaStream_t st) {
+    const int Hs = (H + 1) / 2, Ws = (W + 1) / 2;
+    SMK_REQUIRE(stride == 1 || stride == 2, "stem_ds: stride must be 1 or 2");
+    SMK_REQUIRE(H % 2 == 0 && W % 2 == 0 && Hs % SD_T == 0 && Ws % SD_T == 0, "stem_ds: image size %dx%d must be a multiple of 32", H, W);
+    SMK_REQUIRE(((uintptr_t)img & 7) == 0, "stem_ds: image pointer must be 8-byte aligned");
+    StemDs p{stem_w, stem_s, stem_b, dw_w, dw_s, dw_b, pw_w, pw_s, pw_b, out, round_out};
+    const double px_o = (double)B * (Hs / stride) * (Ws / stride);
+    SMK_TAG("stem_ds_fused", 4.0 * ((double)B * 3 * H * W + px_o * 16 + 27 * 16 + 9 * 16 + 256 + 96),
+            2.0 * ((double)B * Hs * Ws * 16 * 27 + px_o * 16 * (9 + 16)), st);
+    dim3 grid((Hs / SD_T) * (Ws / SD_T), B);
+    if (stride == 1) SMK_LAUNCH((stem_ds_kernel<1>), grid, dim3(256), 0, st, img, H, W, Hs, Ws, same_pad_begin(H, 2), p);
+    else SMK_LAUNCH((stem_ds_kernel<2>), grid, dim3(256), 0, st, img, H, W, Hs, Ws, same_pad_begin(H, 2), p);
+    SMK_CHECK_LAUNCH();
+    return 0;
+}
+
 int maxpool2x2(const float* in, int ld_in, int B, int H, int W, int C, float* out, cudaStream_t st) {
     long total = (long)B * (H / 2) * (W / 2) * (C / 4);
     int blocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
@@ -539,4 +712,12 @@ extern "C" int smk_debug_conv_f32(const float* in, int ld_in, int B, int H, int 
     p.in = in; p.ld_in = ld_in; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.w = w_kn; p.scale = scale; p.bias = bias; p.N = N; p.K = K;
     p.mode = mode; p.relu = relu; p.res = res; p.ld_res = ld_res; p.out = out; p.ld_out = ld_out; p.shuffle = shuffle;
     return smk::conv_gemm(p, (cudaStream_t)stream);
+}
+
+extern "C" int smk_debug_stem_ds(const float* img, int B, int H, int W, const float* stem_w, const float* stem_s, const float* stem_b,
+                                 const float* dw_w, const float* dw_s, const float* dw_b, const float* pw_w, const float* pw_s,
+                                 const float* pw_b, int stride, int round_out, float* out, void* stream) {
+    if (B == 0) return 0;
+    SMK_REQUIRE(img && stem_w && stem_s && stem_b && dw_w && dw_s && dw_b && pw_w && pw_s && pw_b && out, "smk_debug_stem_ds: null argument");
+    return smk::stem_ds(img, B, H, W, stem_w, stem_s, stem_b, dw_w, dw_s, dw_b, pw_w, pw_s, pw_b, stride, round_out, out, (cudaStream_t)stream);
 }

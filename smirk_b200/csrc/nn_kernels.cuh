@@ -38,6 +38,11 @@ int stem_conv(const float* img_nchw, int B, int H, int W, const float* w /*[27][
 // Three 16-channel stems over the same image in one pass (the encoder's three backbones).
 int stem_conv3(const float* img_nchw, int B, int H, int W, const float* const w[3], const float* const scale[3],
                const float* const bias[3], float* const out[3], cudaStream_t st);
+// Fused stem (3x3 s2, 3 -> 16, BN, ReLU) + depthwise-separable block 0 (dw 3x3 s{1,2} + BN + ReLU, 1x1 16 -> 16 + BN,
+// + skip when stride 1) of one backbone: image NCHW fp32 -> [B, 112/stride, 112/stride, 16] NHWC.  pw_w is [ci][co] fp32.
+int stem_ds(const float* img_nchw, int B, int H, int W, const float* stem_w /*[27][16]*/, const float* stem_s, const float* stem_b,
+            const float* dw_w /*[9][16]*/, const float* dw_s, const float* dw_b, const float* pw_w /*[16][16]*/, const float* pw_s,
+            const float* pw_b, int stride, int round_out, float* out, cudaStream_t st);
 int maxpool2x2(const float* in, int ld_in, int B, int H, int W, int C, float* out, cudaStream_t st);
 int nchw_to_nhwc_pad(const float* in, int B, int C, int H, int W, int Cp, float* out, cudaStream_t st);
 // out[b, co, h, w] = sigmoid(bias[co] + sum_c in[b,h,w,c] * w[c][co])   (NHWC -> NCHW)

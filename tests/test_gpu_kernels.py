@@ -283,6 +283,39 @@ def test_conv3_sw_exact_on_small_integers(native_lib):
     assert not bad, "mismatches: %s" % (bad,)
 
 
+# ----------------------------------------------------------------- fused stem + block 0 (nn_kernels.cu stem_ds)
+@pytest.mark.parametrize("B,H,stride", [(2, 224, 1), (2, 224, 2), (3, 64, 1), (1, 32, 2)])
+def test_stem_ds_fused_kernel(native_lib, B, H, stride):
+    """conv_stem 3x3 s2 (TF-SAME) + BN + ReLU -> depthwise 3x3 s{1,2} + BN + ReLU -> 1x1 16->16 + BN (+ skip at
+    stride 1) against torch in float64; fp32 CUDA-core path, so the 1e-4 tolerance of the fp32 encoder applies."""
+    g = torch.Generator().manual_seed(51)
+    dd = torch.float64
+    img = torch.rand(B, 3, H, H, generator=g)
+    ws = torch.randn(16, 3, 3, 3, generator=g) / 27 ** 0.5
+    wd = torch.randn(16, 1, 3, 3, generator=g) / 3.0
+    wp = torch.randn(16, 16, 1, 1, generator=g) / 4.0
+    sb = [(torch.rand(16, generator=g) + 0.5, torch.randn(16, generator=g) * 0.2) for _ in range(3)]
+    bn = lambda t, i: t * sb[i][0].to(dd).view(1, -1, 1, 1) + sb[i][1].to(dd).view(1, -1, 1, 1)
+    s = F.relu(bn(F.conv2d(F.pad(img.to(dd), (0, 1, 0, 1)), ws.to(dd), stride=2), 0))
+    d = F.relu(bn(tf_same_dw(s, wd.to(dd), stride), 1))
+    ref = bn(F.conv2d(d, wp.to(dd)), 2)
+    if stride == 1:
+        ref = ref + s
+    ref = ref.float()
+    Ho = H // 2 // stride
+    t = [img.contiguous().to(DEV), ws.view(16, 27).t().contiguous().to(DEV), sb[0][0].to(DEV), sb[0][1].to(DEV),
+         wd.view(16, 9).t().contiguous().to(DEV), sb[1][0].to(DEV), sb[1][1].to(DEV),
+         wp.view(16, 16).t().contiguous().to(DEV), sb[2][0].to(DEV), sb[2][1].to(DEV)]
+    out = torch.full((B, Ho, Ho, 16), float("nan"), device=DEV)
+    rc = native_lib.smk_debug_stem_ds(P(t[0]), B, H, H, *[P(x) for x in t[1:]], stride, 0, P(out), stream())
+    assert rc == 0, native_lib.smk_last_error()
+    torch.cuda.synchronize()
+    got = out.permute(0, 3, 1, 2).cpu()
+    assert torch.isfinite(got).all(), "unwritten outputs: %d" % int((~torch.isfinite(got)).sum())
+    err = (got - ref).abs().max().item()
+    assert err <= 1e-4 * ref.abs().max().item(), "max err %.3g vs scale %.3g" % (err, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("B,H,W,Cin,N,mode", SW_CASES)
 def test_conv3_sw_random_with_epilogue(native_lib, B, H, W, Cin, N, mode):
     x, w, scale, bias = make_case(B, H, W, Cin, N, 43, mode)
