@@ -179,7 +179,7 @@ def main():
     ap.add_argument("--generator", action="store_true", help="include SmirkGenerator (configs[2], full cycle)")
     ap.add_argument("--cpu-sample", type=int, default=16, help="faces per CPU-baseline pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--slots", type=int, default=3, help="pipeline lanes: consecutive batches alternate over this many stream/graph replicas")
+    ap.add_argument("--slots", type=int, default=4, help="pipeline lanes: consecutive batches alternate over this many stream/graph replicas")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel breakdown JSON here")
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "tf32-unfused"],
                     help="tf32: 1x1/3x3/transposed convs on tcgen05 tensor cores (the reference's own cuDNN default); "

@@ -422,13 +422,16 @@ int tc_conv(const TcConv& p, cudaStream_t st) {
     SMK_REQUIRE(p.store != 1 || ((p.N / 4) % 32 == 0), "tc_conv: pixel-shuffle store needs Cout %% 32 == 0");
     int BN = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
     // Few-tile, deep-K problems (the encoder's 7x7 / 14x14 projections: M = 1568..6272, K up to 960) are a serial
-    // chain of k-blocks on a handful of SMs: narrower N tiles put more CTAs to work and a deeper ring keeps
-    // more TMA loads in flight per CTA.
+    // chain of k-blocks on a handful of SMs: narrower N tiles put more CTAs to work.  An 8-stage ring with one
+    // CTA per SM (SMK_TC_DEEP_SMALL=1) makes such a kernel ~20 % faster when it runs ALONE, but its 177 KB of
+    // shared memory evict every other kernel from the SM; the pipeline runs three backbones x several batches
+    // concurrently, where the small-footprint configuration is worth +11 % end to end (profiles/r01_footprint_sweep.txt).
     const int nkb_all = cdiv(p.K, BK);
     bool deep_small = false;
     if (nkb_all >= 6 && p.store != 1) {
         while (BN > 32 && (long)cdiv(M, BM) * cdiv(p.N, BN) < 148) BN >>= 1;
-        deep_small = (long)cdiv(M, BM) * cdiv(p.N, BN) <= 2 * 148;
+        static const int deep_small_on = []() { const char* e = getenv("SMK_TC_DEEP_SMALL"); return e ? atoi(e) : 0; }();
+        deep_small = deep_small_on && (long)cdiv(M, BM) * cdiv(p.N, BN) <= 2 * 148;
     }
     CUtensorMap tmA, tmB;
     TcArgs a{};
@@ -464,9 +467,12 @@ int tc_conv(const TcConv& p, cudaStream_t st) {
         if (BN == 64) return launch<64, 3, 2, true>(tmA, tmB, a, st);
         return a.nkb > 8 ? launch<128, 5, 1, true>(tmA, tmB, a, st) : launch<128, 2, 2, true>(tmA, tmB, a, st);
     }
-    // Shallow-K layers (the encoder's 1x1 convs) are HBM-bound: a 2-stage ring keeps the footprint small so
-    // 3-5 CTAs share an SM and hide each other's prologue/epilogue; deep-K layers get a deeper ring.
-    const bool shallow = a.nkb <= 2;
+    // One tile per CTA, 2-stage ring: 41-66 KB per CTA, so 3-5 CTAs of this kernel — or CTAs of the other
+    // backbones' and batches' kernels — share an SM and hide each other's prologue/epilogue.  Deeper rings
+    // (SMK_TC_SHALLOW_NKB=2 restores them for K > 64) win a few percent per kernel in isolation and lose
+    // 5 % end to end for the same co-residency reason as above.
+    static const int shallow_nkb = []() { const char* e = getenv("SMK_TC_SHALLOW_NKB"); return e ? atoi(e) : (1 << 30); }();
+    const bool shallow = a.nkb <= shallow_nkb;
     if (BN == 32) return shallow ? launch<32, 2, 5, false>(tmA, tmB, a, st) : launch<32, 4, 2, false>(tmA, tmB, a, st);
     if (BN == 64) return shallow ? launch<64, 2, 4, false>(tmA, tmB, a, st) : launch<64, 4, 2, false>(tmA, tmB, a, st);
     return shallow ? launch<128, 2, 3, false>(tmA, tmB, a, st) : launch<128, 3, 2, false>(tmA, tmB, a, st);

@@ -159,6 +159,7 @@ raster_tile_kernel(RenderDev d, const float* __restrict__ recs, const uint32_t* 
             bool hit = (c[k] & 0xFF) <= tx && tx <= ((c[k] >> 8) & 0xFF) && ((c[k] >> 16) & 0xFF) <= ty && ty <= (c[k] >> 24);
             hits |= (hit ? 1u : 0u) << k;
         }
+        if (__ballot_sync(0xffffffffu, hits != 0) == 0) continue;      // warp-uniform: a tile sees ~1 % of the faces
         const int lane = tid & 31;
         const int mine = __popc(hits);
         int incl = mine;                                      // inclusive warp scan of the per-lane hit counts

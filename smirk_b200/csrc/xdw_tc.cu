@@ -281,8 +281,10 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                 const int ey = ey0 + half * 8 + (r >> 4), ex = ex0 + (r & 15);
                 const bool inside = ey >= 0 && ey < a.H && ex >= 0 && ex < a.W;
                 float* erow = E + (size_t)(half * 128 + r) * E_PITCH;
+                const int nquads = (min(NC, a.mid - ch0) + 3) >> 2;      // channel quads of this chunk that exist (phase (b) reads no others)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
+                    if (j >= nquads) break;
                     const float4 sc = *reinterpret_cast<const float4*>(par + 4 * j);
                     const float4 bi = *reinterpret_cast<const float4*>(par + NC + 4 * j);
                     float4 o = fma4(v[j], sc, bi);
@@ -407,11 +409,12 @@ int xdw_conv(const XdwConv& p, cudaStream_t st) {
                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SMK_REQUIRE(r == CUDA_SUCCESS, "xdw_conv: cuTensorMapEncodeTiled(w1) failed (%d): mid=%d Cin=%d", (int)r, p.mid, p.Cin);
     }
+    static const int slots = []() { const char* e = getenv("SMK_XDW_SLOTS"); return e ? atoi(e) : 148; }();   // resident CTAs to aim for: one per SM leaves half of every SM to concurrent kernels (+4 % end to end vs 296)
     XdwArgs a{};
     a.H = p.H; a.W = p.W; a.Ho = Ho; a.Wo = Wo; a.mid = p.mid; a.nkb = cdiv(p.Cin, BK); a.nchunks = cdiv(p.mid, NC);
     {   // split the channel chunks over enough CTAs to fill 148 SMs x 2 CTAs
         const long tiles = (long)cdiv(Wo, TO) * cdiv(Ho, TO) * p.B;
-        int groups = (int)std::min<long>(a.nchunks, std::max<long>(1, (2 * 148 + tiles - 1) / tiles));
+        int groups = (int)std::min<long>(a.nchunks, std::max<long>(1, (slots + tiles - 1) / tiles));
         a.chunks_per_group = cdiv(a.nchunks, groups);
         a.groups = cdiv(a.nchunks, a.chunks_per_group);
     }
@@ -435,7 +438,7 @@ int xdw_conv(const XdwConv& p, cudaStream_t st) {
         SMK_TAG(tag, 4.0 * (px_in * p.Cin + px_out * p.mid + (double)p.mid * (p.Cin + 13)), 2.0 * px_in * p.Cin * p.mid + 18.0 * px_out * p.mid, st);
     }
     a.n_items = a.tiles_x * a.tiles_y * p.B * a.groups;
-    dim3 grid((unsigned)std::min(a.n_items, 2 * 148));          // persistent: 2 CTAs per SM
+    dim3 grid((unsigned)std::min(a.n_items, slots));            // persistent: (up to) 2 CTAs per SM
     if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1>), dim3(grid), dim3(NUM_THREADS), smem, st, tmX, tmW, a);
     else SMK_LAUNCH((xdw_kernel<2>), dim3(grid), dim3(NUM_THREADS), smem, st, tmX, tmW, a);
     SMK_CHECK_LAUNCH();
