@@ -247,7 +247,10 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
                 rc = smk::dwconv3x3(x, B, res, res, b.cin, b.stride, b.dw.w, b.dw.scale, b.dw.bias, d, st, h->precision == 1);
                 if (!rc) rc = pointwise(b.pw, d, B, ro, ro, false, b.skip ? x : nullptr, y, st);
             } else if (b.kind == IR) {
-                if (h->fuse_xdw && b.pw.wt) {
+                // The 7x7 layers (a 16x16 window holds 81 useful pixels, 49 outputs) run 3 % faster end to end as
+                // 1x1 GEMM + depthwise kernels; every other resolution wins fused (profiles/r01_footprint_sweep.txt).
+                static const int xdw_min_res = []() { const char* e = getenv("SMK_XDW_MIN_RES"); return e ? atoi(e) : 8; }();
+                if (h->fuse_xdw && b.pw.wt && res >= xdw_min_res) {
                     // expand 1x1 + depthwise 3x3 in one kernel: the expanded tensor never leaves the SM
                     smk::XdwConv q{};
                     q.x = x; q.B = B; q.H = res; q.W = res; q.Cin = b.cin; q.w1t = b.pw.wt; q.scale1 = b.pw.scale; q.bias1 = b.pw.bias;

@@ -429,7 +429,10 @@ int tc_conv(const TcConv& p, cudaStream_t st) {
     const int nkb_all = cdiv(p.K, BK);
     bool deep_small = false;
     if (nkb_all >= 6 && p.store != 1) {
-        while (BN > 32 && (long)cdiv(M, BM) * cdiv(p.N, BN) < 148) BN >>= 1;
+        // (narrowing is off by default: fewer, wider tiles re-read A less often, and in the concurrent pipeline idle SMs
+        //  are filled by other kernels anyway; SMK_TC_NARROW=148 restores the latency-oriented choice.)
+        static const int narrow_target = []() { const char* e = getenv("SMK_TC_NARROW"); return e ? atoi(e) : 0; }();
+        while (BN > 32 && (long)cdiv(M, BM) * cdiv(p.N, BN) < narrow_target) BN >>= 1;
         static const int deep_small_on = []() { const char* e = getenv("SMK_TC_DEEP_SMALL"); return e ? atoi(e) : 0; }();
         deep_small = deep_small_on && (long)cdiv(M, BM) * cdiv(p.N, BN) <= 2 * 148;
     }

@@ -282,15 +282,22 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                 const bool inside = ey >= 0 && ey < a.H && ex >= 0 && ex < a.W;
                 float* erow = E + (size_t)(half * 128 + r) * E_PITCH;
                 const int nquads = (min(NC, a.mid - ch0) + 3) >> 2;      // channel quads of this chunk that exist (phase (b) reads no others)
+                if (inside) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (j >= nquads) break;
-                    const float4 sc = *reinterpret_cast<const float4*>(par + 4 * j);
-                    const float4 bi = *reinterpret_cast<const float4*>(par + NC + 4 * j);
-                    float4 o = fma4(v[j], sc, bi);
-                    o.x = inside ? fmaxf(o.x, 0.f) : 0.f; o.y = inside ? fmaxf(o.y, 0.f) : 0.f;
-                    o.z = inside ? fmaxf(o.z, 0.f) : 0.f; o.w = inside ? fmaxf(o.w, 0.f) : 0.f;
-                    *reinterpret_cast<float4*>(erow + 4 * j) = o;
+                    for (int j = 0; j < 8; ++j) {
+                        if (j >= nquads) break;
+                        const float4 sc = *reinterpret_cast<const float4*>(par + 4 * j);
+                        const float4 bi = *reinterpret_cast<const float4*>(par + NC + 4 * j);
+                        float4 o = fma4(v[j], sc, bi);
+                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                        *reinterpret_cast<float4*>(erow + 4 * j) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j >= nquads) break;
+                        *reinterpret_cast<float4*>(erow + 4 * j) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
             }
             tcgen05_fence_before();
