@@ -39,7 +39,10 @@ void prof_begin(const char* tag, double bytes, double flops, cudaStream_t st) {
     g_pending = true; g_pending_stream = st;
 }
 bool profiling() { return g_prof; }
-bool pdl_enabled() { static const bool on = []() { const char* e = getenv("SMK_PDL"); return !e || atoi(e) != 0; }(); return on; }
+// Off by default: with 3 backbone streams x 4 batches in flight the launch gaps are already filled by other
+// kernels and programmatic edges measured neutral-to-slightly-negative end to end (profiles/r01_footprint_sweep.txt);
+// SMK_PDL=1 turns the launch attribute on (useful for a single low-latency stream: +3 % at one lane).
+bool pdl_enabled() { static const bool on = []() { const char* e = getenv("SMK_PDL"); return e && atoi(e) != 0; }(); return on; }
 void prof_end() {
     if (!g_prof || !g_pending) return;
     cudaEventRecord(g_entries.back().b, g_pending_stream);

@@ -76,8 +76,8 @@ static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 // launch_dependents` lets the following kernel's CTAs be scheduled as soon as all CTAs of this one have
 // started.  Net effect: launch latency, parameter/tensor-map fetch, barrier init and TMEM allocation of
 // kernel N+1 overlap the tail of kernel N — which is what a chain of ~100 short kernels per batch is bound
-// by.  Inside a stream capture these become programmatic graph edges.  SMK_PDL=0 disables the attribute
-// (the device-side instructions are then no-ops).
+// by.  Inside a stream capture these become programmatic graph edges.  The attribute is opt-in (SMK_PDL=1, see
+// common.cu); without it the device-side instructions are no-ops.
 bool pdl_enabled();
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_sync() {

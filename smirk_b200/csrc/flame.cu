@@ -377,7 +377,8 @@ extern "C" int smk_flame_forward(const SmkFlame* h, const float* betas, const fl
     SMK_LAUNCH(flame_pose_kernel, dim3(B), dim3(128), 0, st, d, betas, full_pose, B, A, pf, joints, dyn);
     SMK_CHECK_LAUNCH();
     int rc;
-    if (B >= 96) rc = launch_verts<8>(d, betas, eyelid, A, pf, B, verts, st);
+    static const int bt8_from = []() { const char* e = getenv("SMK_FLAME_BT8_FROM"); return e ? atoi(e) : 96; }();
+    if (B >= bt8_from) rc = launch_verts<8>(d, betas, eyelid, A, pf, B, verts, st);
     else if (B >= 8) rc = launch_verts<4>(d, betas, eyelid, A, pf, B, verts, st);
     else if (B >= 2) rc = launch_verts<2>(d, betas, eyelid, A, pf, B, verts, st);
     else rc = launch_verts<1>(d, betas, eyelid, A, pf, B, verts, st);

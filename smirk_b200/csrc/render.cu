@@ -149,10 +149,17 @@ raster_tile_kernel(RenderDev d, const float* __restrict__ recs, const uint32_t* 
     //    (4 packed ranges per thread per pass: one 16-byte load, one shared atomic per warp)
     const uint4* rg4 = reinterpret_cast<const uint4*>(ranges + (size_t)b * d.F);
     const int F4 = d.F >> 2;                                  // F % 4 == 0 is checked at create time
-    for (int base = 0; base < F4; base += nthr) {
-        const int i4 = base + tid;
-        uint32_t c[4] = {0xFFu, 0xFFu, 0xFFu, 0xFFu};
-        if (i4 < F4) { uint4 v = __ldg(rg4 + i4); c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w; }
+    for (int base0 = 0; base0 < F4; base0 += 4 * nthr) {
+      uint4 pre[4];                                           // four independent 16-byte loads in flight: one L2 round trip per 4 passes
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+          const int j4 = base0 + u * nthr + tid;
+          pre[u] = j4 < F4 ? __ldg(rg4 + j4) : make_uint4(0xFFu, 0xFFu, 0xFFu, 0xFFu);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i4 = base0 + u * nthr + tid;
+        const uint32_t c[4] = {pre[u].x, pre[u].y, pre[u].z, pre[u].w};
         unsigned hits = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -172,6 +179,7 @@ raster_tile_kernel(RenderDev d, const float* __restrict__ recs, const uint32_t* 
         int pos = wbase + incl - mine;
 #pragma unroll
         for (int k = 0; k < 4; ++k) if (hits & (1u << k)) s_cand[pos++] = (uint16_t)(i4 * 4 + k);
+      }
     }
     __syncthreads();
     const int ncand = s_count;
