@@ -416,7 +416,9 @@ int xdw_conv(const XdwConv& p, cudaStream_t st) {
                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SMK_REQUIRE(r == CUDA_SUCCESS, "xdw_conv: cuTensorMapEncodeTiled(w1) failed (%d): mid=%d Cin=%d", (int)r, p.mid, p.Cin);
     }
-    static const int slots = []() { const char* e = getenv("SMK_XDW_SLOTS"); return e ? atoi(e) : 148; }();   // resident CTAs to aim for: one per SM leaves half of every SM to concurrent kernels (+4 % end to end vs 296)
+    static const int slots_lo = []() { const char* e = getenv("SMK_XDW_SLOTS"); return e ? atoi(e) : 148; }();   // resident CTAs to aim for: one per SM leaves half of every SM to concurrent kernels (+4 % end to end vs 296)
+    static const int slots_hi = []() { const char* e = getenv("SMK_XDW_SLOTS_HI"); return e ? atoi(e) : 0; }();  // layers with >= 296 output tiles (0: same as SMK_XDW_SLOTS)
+    const int slots = (slots_hi > 0 && (long)cdiv(Wo, TO) * cdiv(Ho, TO) * p.B >= 296) ? slots_hi : slots_lo;
     XdwArgs a{};
     a.H = p.H; a.W = p.W; a.Ho = Ho; a.Wo = Wo; a.mid = p.mid; a.nkb = cdiv(p.Cin, BK); a.nchunks = cdiv(p.mid, NC);
     {   // split the channel chunks over enough CTAs to fill 148 SMs x 2 CTAs

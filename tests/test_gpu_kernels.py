@@ -111,6 +111,9 @@ TC_CASES = [
     (2, 14, 14, 64, 128, 1),        # 3x3, tiles cross rows and images, partial tail
     (3, 14, 14, 32, 96, 2),         # 3x3 over a reflection-padded buffer
     (2, 28, 28, 128, 256, 1),       # 3x3, two N tiles, 36 k-blocks (ring wraps many times)
+    (2, 160, 160, 32, 32, 1),       # 3x3 persistent path: 400 tiles on 296 CTAs -> CTAs own 1 or 2 tiles (TMEM double buffer)
+    (3, 120, 120, 64, 64, 2),       # 3x3 persistent, BN = 64, reflection-padded input, 338 tiles
+    (1, 300, 300, 32, 24, 1),       # 3x3 persistent, 704 tiles -> 2-3 tiles per CTA, N < BN, partial last tile
 ]
 
 
