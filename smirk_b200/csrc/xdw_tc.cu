@@ -31,7 +31,10 @@ constexpr int HALF_BYTES = 128 * BKB;           // one 16x8-pixel box, 32 channe
 constexpr int NC = 32;                          // expanded channels per chunk
 constexpr int B_BYTES = NC * BKB;               // 4 KiB
 constexpr int STAGE_BYTES = 2 * HALF_BYTES + B_BYTES;   // 36 KiB
-constexpr int STAGES = 2;
+#ifndef SMK_XDW_STAGES
+#define SMK_XDW_STAGES 2
+#endif
+constexpr int STAGES = SMK_XDW_STAGES;
 constexpr int E_PITCH = NC + 4;                 // floats; 144-byte rows (odd multiple of 16 B): conflict-free 16-byte column writes
 constexpr int E_BYTES = 256 * E_PITCH * 4;      // 36 864 B
 constexpr int PAR_ROWS = 13;                     // scale1, bias1, 9 depthwise taps, scale2, bias2
