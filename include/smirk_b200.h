@@ -155,6 +155,23 @@ int smk_generator_forward(const SmkGenerator* h, const float* x, int B, float* y
                           void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Crop / warp front and back end — replaces the CPU `skimage.transform.warp` calls of
+ * demo.py:97 and demo_video.py:128,149 (+ BGR->RGB, /255, HWC->CHW of demo.py:103-105) for frames that are
+ * already on the device.  Bilinear (order 1), mode 'constant', cval 0, clip to the source range, float64
+ * arithmetic, truncation to uint8 — skimage's `_warp_fast` semantics.  m / minv: [B][9] row-major float64 3x3
+ * maps from OUTPUT pixel (col,row,1) to INPUT (x,y,1) (affine rows only); ws >= smk_warp_workspace_bytes(B).
+ *   smk_crop_warp      : frames uint8 [B,H,W,3] -> out float32 [B,3,S,S] = uint8 result / 255; swap_rb reverses the
+ *                        channel order (BGR frame -> RGB tensor).
+ *   smk_warp_u8        : src uint8 [B,Hs,Ws,3] -> dst uint8 [B,Hd,Wd,3].
+ *   smk_f32chw_to_u8hwc: (x * 255.0f).astype(uint8) of a [B,3,S,S] float image -> [B,S,S,3] (demo_video.py:148).  */
+size_t smk_warp_workspace_bytes(int B);
+int smk_crop_warp(const uint8_t* frames, int B, int H, int W, const double* minv, int S, int swap_rb, float* out,
+                  void* ws, size_t ws_bytes, void* stream);
+int smk_warp_u8(const uint8_t* src, int B, int Hs, int Ws, const double* m, int Hd, int Wd, uint8_t* dst,
+                void* ws, size_t ws_bytes, void* stream);
+int smk_f32chw_to_u8hwc(const float* in, int B, int S, uint8_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Kernel-level test entry points (used by tests/ to check single convolution kernels against torch;
  * not part of the drop-in surface).  All pointers are device pointers.
  *   smk_debug_conv_f32: fp32 CUDA-core implicit GEMM.  w_kn is [K][N]; mode 0 = 1x1, 1 = 3x3 zero pad,

@@ -51,7 +51,8 @@ SYMBOLS = ["smk_version", "smk_last_error", "smk_launch_count", "smk_profiler_en
            "smk_project_points",
            "smk_encoder_create", "smk_encoder_destroy", "smk_encoder_workspace_bytes", "smk_encoder_forward",
            "smk_generator_create", "smk_generator_destroy", "smk_generator_workspace_bytes", "smk_generator_forward",
-           "smk_debug_conv_f32", "smk_debug_conv_tc", "smk_debug_reflect_halo", "smk_debug_xdw", "smk_debug_conv3_sw", "smk_debug_stem_ds"]
+           "smk_debug_conv_f32", "smk_debug_conv_tc", "smk_debug_reflect_halo", "smk_debug_xdw", "smk_debug_conv3_sw", "smk_debug_stem_ds",
+           "smk_warp_workspace_bytes", "smk_crop_warp", "smk_warp_u8", "smk_f32chw_to_u8hwc"]
 
 
 def lib():
@@ -98,6 +99,11 @@ def lib():
     L.smk_debug_reflect_halo.argtypes = [vp, i, i, i, i, vp]
     L.smk_debug_conv3_sw.argtypes = [vp, i, i, i, i, i, vp, vp, vp, i, i, i, vp, i, i, vp, i, i, vp]
     L.smk_debug_xdw.argtypes = [vp, i, i, i, i, vp, vp, vp, i, vp, vp, vp, i, i, vp, vp]
+    L.smk_warp_workspace_bytes.argtypes = [i]
+    L.smk_warp_workspace_bytes.restype = C.c_size_t
+    L.smk_crop_warp.argtypes = [vp, i, i, i, vp, i, i, vp, vp, C.c_size_t, vp]
+    L.smk_warp_u8.argtypes = [vp, i, i, i, vp, i, i, vp, vp, C.c_size_t, vp]
+    L.smk_f32chw_to_u8hwc.argtypes = [vp, i, i, vp, vp]
     L.smk_debug_stem_ds.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, vp, vp]
     if L.smk_version() != 100:
         raise RuntimeError("smirk_b200: library/header version mismatch (%d)" % L.smk_version())
