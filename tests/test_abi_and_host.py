@@ -93,3 +93,25 @@ def test_synthetic_assets_are_deterministic(asset_root, tmp_path):
     m2 = synth_assets.synthetic_flame_model(b["verts"], b["faces"].astype(np.int64), seed=0)
     assert np.array_equal(m1["shapedirs"], m2["shapedirs"]) and m1["shapedirs"].shape == (5023, 3, 400)
     assert np.allclose(m1["weights"].sum(1), 1) and np.allclose(m1["J_regressor"].sum(1), 1)
+
+
+def test_ncu_traffic_tool_parses_an_ncu_csv(tmp_path):
+    """tools/ncu_traffic.py (feeds bench.py's roofline.traffic): kernel-name -> tag mapping, unit scaling, --last-pass."""
+    import json
+    import subprocess
+    import sys
+    rows = ['"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"']
+    kernels = ["void smk::<unnamed>::xdw_kernel<1>(CUtensorMap_st)", "void smk::<unnamed>::gemm_tc_kernel<32, 2, 5, 0>(CUtensorMap_st)",
+               "void at::native::vectorized_elementwise_kernel<4>()", "void smk::<unnamed>::xdw_kernel<2>(CUtensorMap_st)"]
+    for i, k in enumerate(kernels):
+        for metric, unit, val in (("dram__bytes_read.sum", "Mbyte", "2.5"), ("dram__bytes_write.sum", "Kbyte", "500"), ("gpu__time_duration.sum", "us", "10")):
+            rows.append('"%d","1","python","h","%s","1","7","(320, 1, 1)","(148, 1, 1)","0","10.0","Cmd","%s","%s","%s"' % (i, k, metric, unit, val))
+    src, out = tmp_path / "n.csv", tmp_path / "t.json"
+    src.write_text("==PROF== Connected\n" + "\n".join(rows) + "\n")
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "ncu_traffic.py")
+    subprocess.check_call([sys.executable, tool, str(src), str(out)], stdout=subprocess.DEVNULL)
+    d = json.load(open(out))["kernels"]
+    assert set(d) == {"xdw_fused_tc", "pw_gemm_tc"} and d["xdw_fused_tc"]["launches"] == 2
+    assert abs(d["xdw_fused_tc"]["traffic_bytes_per_launch"] - 3.0e6) < 1 and abs(d["pw_gemm_tc"]["ncu_us"] - 10.0) < 1e-9
+    subprocess.check_call([sys.executable, tool, str(src), str(out), "--last-pass", "1"], stdout=subprocess.DEVNULL)
+    assert set(json.load(open(out))["kernels"]) == {"xdw_fused_tc"}
