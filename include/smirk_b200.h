@@ -172,6 +172,27 @@ int smk_warp_u8(const uint8_t* src, int B, int Hs, int Ws, const double* m, int 
 int smk_f32chw_to_u8hwc(const float* in, int B, int S, uint8_t* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Masking between Renderer and SmirkGenerator (src/utils/masking.py, demo.py:138-167).
+ * WORK IN PROGRESS (branch wip/masking-kernels): not yet validated on a GPU.
+ * Random draws stay with the caller (torch); these entry points are the deterministic parts.
+ *   face_weights: trans_verts [B,V,3], base_prob [F] -> weights [B,F]               (masking.py:146-160)
+ *   points      : face_idx int64 [B,N], bary [B,N,3] -> npoints int64 [B,N,2] (x,y)  (masking.py:166-174)
+ *   compose     : img [B,3,S,S], hull [B,1,S,S], npoints/rbound (first rbound[b] points are kept), optional
+ *                 rendered_mask [B,1,S,S], noise_mult [B,3,S,S], random_centres [B,1,S,S] -> masked [B,3,S,S]  */
+typedef struct SmkMasking SmkMasking;
+typedef struct { int n_verts; int n_faces; const int32_t* faces; } SmkMaskingDesc;
+int smk_masking_create(const SmkMaskingDesc* desc, SmkMasking** out);
+void smk_masking_destroy(SmkMasking* h);
+size_t smk_masking_workspace_bytes(const SmkMasking* h, int B, int S);
+int smk_masking_face_weights(const SmkMasking* h, const float* trans_verts, const float* base_prob, int B,
+                             float* weights, void* ws, size_t ws_bytes, void* stream);
+int smk_masking_points(const SmkMasking* h, const float* trans_verts, const int64_t* face_idx, const float* bary,
+                       int B, int N, int image_size, int64_t* npoints, void* stream);
+int smk_masking_compose(const SmkMasking* h, const float* img, const float* hull, const int64_t* npoints, const int64_t* rbound,
+                        int N, const float* rendered_mask, const float* noise_mult, const float* random_centres,
+                        int wr, int B, int S, float* masked, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Kernel-level test entry points (used by tests/ to check single convolution kernels against torch;
  * not part of the drop-in surface).  All pointers are device pointers.
  *   smk_debug_conv_f32: fp32 CUDA-core implicit GEMM.  w_kn is [K][N]; mode 0 = 1x1, 1 = 3x3 zero pad,

@@ -52,7 +52,9 @@ SYMBOLS = ["smk_version", "smk_last_error", "smk_launch_count", "smk_profiler_en
            "smk_encoder_create", "smk_encoder_destroy", "smk_encoder_workspace_bytes", "smk_encoder_forward",
            "smk_generator_create", "smk_generator_destroy", "smk_generator_workspace_bytes", "smk_generator_forward",
            "smk_debug_conv_f32", "smk_debug_conv_tc", "smk_debug_reflect_halo", "smk_debug_xdw", "smk_debug_conv3_sw", "smk_debug_stem_ds",
-           "smk_warp_workspace_bytes", "smk_crop_warp", "smk_warp_u8", "smk_f32chw_to_u8hwc"]
+           "smk_warp_workspace_bytes", "smk_crop_warp", "smk_warp_u8", "smk_f32chw_to_u8hwc",
+           "smk_masking_create", "smk_masking_destroy", "smk_masking_workspace_bytes", "smk_masking_face_weights",
+           "smk_masking_points", "smk_masking_compose"]
 
 
 def lib():
@@ -99,6 +101,12 @@ def lib():
     L.smk_debug_reflect_halo.argtypes = [vp, i, i, i, i, vp]
     L.smk_debug_conv3_sw.argtypes = [vp, i, i, i, i, i, vp, vp, vp, i, i, i, vp, i, i, vp, i, i, vp]
     L.smk_debug_xdw.argtypes = [vp, i, i, i, i, vp, vp, vp, i, vp, vp, vp, i, i, vp, vp]
+    L.smk_masking_create.argtypes = [vp, vp]
+    L.smk_masking_destroy.argtypes = [vp]
+    L.smk_masking_workspace_bytes.argtypes = [vp, i, i]
+    L.smk_masking_face_weights.argtypes = [vp, vp, vp, i, vp, vp, sz, vp]
+    L.smk_masking_points.argtypes = [vp, vp, vp, vp, i, i, i, vp, vp]
+    L.smk_masking_compose.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, i, i, i, vp, vp, sz, vp]
     L.smk_warp_workspace_bytes.argtypes = [i]
     L.smk_warp_workspace_bytes.restype = C.c_size_t
     L.smk_crop_warp.argtypes = [vp, i, i, i, vp, i, i, vp, vp, C.c_size_t, vp]
