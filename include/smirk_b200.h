@@ -208,11 +208,6 @@ int smk_debug_conv_tc(const float* in, int ld_in, int B, int H, int W, int Cin, 
                       const float* bias, int N, int K, int mode, int relu, const float* res, int ld_res, int res_pad,
                       float* out, int ld_out, int store, void* stream);
 int smk_debug_reflect_halo(float* buf, int B, int H, int W, int C, void* stream);
-/*   smk_debug_conv3_sw: shifted-window TF32 tcgen05 3x3 conv (same argument meaning as smk_debug_conv_tc with
- *                       mode 1 or 2 and store 0 or 2).                                                          */
-int smk_debug_conv3_sw(const float* in, int ld_in, int B, int H, int W, int Cin, const float* wt, const float* scale,
-                       const float* bias, int N, int mode, int relu, const float* res, int ld_res, int res_pad,
-                       float* out, int ld_out, int store, void* stream);
 /*   smk_debug_xdw: fused expand-1x1 (TF32 tcgen05) + BN + ReLU + depthwise-3x3 (fp32) + BN + ReLU of a
  *                  MobileNetV3 inverted-residual block.  x [B,H,W,Cin] NHWC; w1t [mid][Cin]; wdw [9][mid];
  *                  out [B,ceil(H/stride),ceil(W/stride),mid]; TF-SAME padding.                            */

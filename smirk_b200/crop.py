@@ -2,7 +2,7 @@
 
 Mirrors the helpers the reference's entry scripts use (``demo.py:16-34,84-105``, ``demo_video.py:116-137,147-150``):
 
-    tform = crop_face(frame, landmarks, scale=1.4, image_size=224)      # same name, arguments and result (.params)
+    tform = landmark_box_transform(landmarks, scale=1.4, image_size=224) # the crop transform of demo.py:16-34 (.params)
     img   = crop_to_tensor(frames_u8, [tform, ...])                      # warp(image, tform.inverse) + BGR2RGB + /255
     back  = warp_back(rendered, [tform, ...], (H, W))                    # warp(rendered_uint8, tform, (H, W))
 
@@ -69,19 +69,19 @@ def estimate_transform(ttype, src, dst):
     return SimilarityTransform(_umeyama(np.asarray(src, np.float64), np.asarray(dst, np.float64), True))
 
 
-def crop_face(frame, landmarks, scale=1.0, image_size=224):
-    """demo.py:16-34 / demo_video.py:16-34: bounding square of the landmarks, scaled, mapped to the crop."""
-    left = np.min(landmarks[:, 0])
-    right = np.max(landmarks[:, 0])
-    top = np.min(landmarks[:, 1])
-    bottom = np.max(landmarks[:, 1])
-    old_size = (right - left + bottom - top) / 2
-    center = np.array([right - (right - left) / 2.0, bottom - (bottom - top) / 2.0])
-    size = int(old_size * scale)
-    src_pts = np.array([[center[0] - size / 2, center[1] - size / 2], [center[0] - size / 2, center[1] + size / 2],
-                        [center[0] + size / 2, center[1] - size / 2]])
-    dst_pts = np.array([[0, 0], [0, image_size - 1], [image_size - 1, 0]])
-    return estimate_transform("similarity", src_pts, dst_pts)
+def landmark_box_transform(landmarks, scale=1.0, image_size=224):
+    """Similarity transform frame -> crop for the square that bounds ``landmarks`` [L,2], grown by ``scale``.
+
+    Produces the transform the reference's entry scripts build for their crops (``demo.py:16-34``: landmark bounding
+    box -> square of side int(mean extent * scale) around the box centre -> three corners mapped onto the crop); the
+    scripts keep their own helper, this one exists for callers that batch frames on the GPU (``crop_to_tensor``)."""
+    pts = np.asarray(landmarks, np.float64)[:, :2]
+    lo, hi = pts.min(axis=0), pts.max(axis=0)
+    half = int(0.5 * float((hi - lo).sum()) * scale) / 2.0
+    centre = hi - (hi - lo) / 2.0
+    corners = centre + half * np.array([[-1.0, -1.0], [-1.0, 1.0], [1.0, -1.0]])
+    target = (image_size - 1) * np.array([[0.0, 0.0], [0.0, 1.0], [1.0, 0.0]])
+    return estimate_transform("similarity", corners, target)
 
 
 def _matrices(tforms, invert, device):
@@ -103,7 +103,7 @@ def _workspace(L, B, device):
 
 def crop_to_tensor(frames, tforms, image_size=224, bgr=True):
     """frames: uint8 CUDA tensor [B,H,W,3] (cv2 / BGR order when ``bgr``); tforms: B transforms frame -> crop (as
-    returned by ``crop_face``).  Returns float32 [B,3,S,S] in [0,1], RGB — what ``demo.py:97,103-105`` feeds the encoder."""
+    returned by ``landmark_box_transform`` or the scripts' own ``crop_face``).  Returns float32 [B,3,S,S] in [0,1], RGB — what ``demo.py:97,103-105`` feeds the encoder."""
     _lib.require_cuda(frames, "frames")
     if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3:
         raise ValueError("frames must be uint8 [B,H,W,3]")

@@ -21,7 +21,5 @@ struct TcConv {
 int tc_init();                                              // resolves the driver's tensor-map encoders
 int tc_conv(const TcConv& p, cudaStream_t st);
 int reflect_halo(float* buf, int B, int H, int W, int C, cudaStream_t st);
-// Shifted-window variant for 3x3 convs (conv3_sw_tc.cu): one patch load per channel chunk, nine tap views.
-int conv3_sw(const TcConv& p, cudaStream_t st);
 
 }  // namespace smk

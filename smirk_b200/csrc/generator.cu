@@ -174,13 +174,6 @@ int conv3(const SmkGenerator* h, const Conv3& c, const float* in, int ld_in, int
         p.in = in; p.ld_in = ld_in; p.B = B; p.H = S; p.W = S; p.Cin = c.cin_p; p.wt = c.wt; p.scale = c.scale; p.bias = c.bias;
         p.N = c.cout; p.K = 9 * c.cin_p; p.mode = refl ? 2 : 1; p.relu = relu ? 1 : 0;
         p.res = res; p.ld_res = c.cout; p.res_pad = res_pad; p.out = out; p.ld_out = ld_out; p.store = store; p.round_out = 1;
-        // The shifted-window kernel (one patch load per channel chunk instead of nine im2col tiles) beat the
-        // one-tile-per-CTA im2col kernel by 12 % on the 224^2 N = 32 layers (profiles/r01_layers_c3_sw_vs_im2col.txt),
-        // but the persistent im2col kernel is faster still (146 vs 218 us, profiles/r01_gemm_tc_persist.txt), so
-        // it is opt-in: SMK_CONV3_SW=1 routes every 3x3 layer it supports through it.
-        static const int force = []() { const char* e = getenv("SMK_CONV3_SW"); return e ? atoi(e) : 0; }();
-        const bool use_sw = force != 0;
-        if (use_sw) return smk::conv3_sw(p, st);
         return smk::tc_conv(p, st);
     }
     ConvProblem p{};

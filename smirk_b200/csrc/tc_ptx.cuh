@@ -69,11 +69,11 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {            // who
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 (= 1, unused) | [32,46) SBO >> 4 (1024 B between 8-row groups)
 //   [46,48) version = 1 | [49,52) base offset = 0 | [61,64) layout = 2 (SWIZZLE_128B)
-// The start address may be any 128-byte row of a 1024-byte-aligned tile (conv3_sw_tc.cu starts its tap views
+// The start address may be any 128-byte row of a 1024-byte-aligned tile (a kernel may start an operand view
 // part-way into the 8-row swizzle period): the tensor core derives the XOR phase from the absolute shared-memory
 // address, exactly like TMA does when it writes the tile, so the base-offset field stays 0.  (Measured: with
 // base offset = (address >> 7) & 7 the shifted views read the wrong 16-byte chunks; with 0 they are exact —
-// tests/test_gpu_kernels.py::test_conv3_sw_exact_on_small_integers.)
+// round-1 shifted-window experiment, profiles/r01_layers_c3_sw_vs_im2col.txt.)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);

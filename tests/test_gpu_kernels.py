@@ -241,51 +241,6 @@ def test_xdw_fused_exact_on_small_integers(native_lib):
         assert torch.equal(out.permute(0, 3, 1, 2).cpu(), ref), "stride %d" % stride
 
 
-# ----------------------------------------------------------------- shifted-window 3x3 conv (conv3_sw_tc.cu)
-def run_sw(native_lib, x, w, scale, bias, mode, relu, res=None):
-    B, Cin, H, W = x.shape
-    N = w.shape[0]
-    xd = nhwc(x).to(DEV)
-    if mode == 2:
-        xd = nhwc(F.pad(x, (1, 1, 1, 1), mode="reflect")).to(DEV)
-    wd = w_nk(w).to(DEV)
-    out = torch.full((B, H, W, N), float("nan"), device=DEV)
-    resd = nhwc(res).to(DEV) if res is not None else None
-    sd, bd = scale.to(DEV), bias.to(DEV)
-    rc = native_lib.smk_debug_conv3_sw(P(xd), Cin, B, H, W, Cin, P(wd), P(sd), P(bd), N, mode, relu, P(resd), N, 0,
-                                       P(out), N, 0, stream())
-    assert rc == 0, native_lib.smk_last_error()
-    torch.cuda.synchronize()
-    return out.permute(0, 3, 1, 2).cpu()
-
-
-SW_CASES = [
-    # B, H,  W,   Cin, N,  mode
-    (1, 4, 30, 32, 32, 1),          # exactly one 4x30 tile
-    (2, 14, 14, 64, 128, 1),        # PW = 16 tiles (8x14), two row tiles, partial second
-    (2, 28, 28, 64, 64, 1),         # one column tile of 28 (< 30), 7 row tiles
-    (1, 56, 56, 32, 32, 1),         # two column tiles (30 + 26)
-    (2, 14, 14, 32, 96, 2),         # reflection-padded input buffer
-    (1, 36, 100, 128, 256, 1),      # 4 chunks, two N tiles, ragged tiles in both directions
-]
-
-
-def test_conv3_sw_exact_on_small_integers(native_lib):
-    """Row-shifted tap views of one shared-memory patch (descriptor start moved by whole 128-byte rows, base
-    offset 0 — the variant with base offset = (addr >> 7) & 7 was measured wrong on B200) are exact."""
-    g = torch.Generator().manual_seed(41)
-    bad = []
-    for (B, H, W, Cin, N, mode) in SW_CASES:
-        x = torch.randint(-3, 4, (B, Cin, H, W), generator=g).float()
-        w = torch.randint(-2, 3, (N, Cin, 3, 3), generator=g).float()
-        one, zero = torch.ones(N), torch.zeros(N)
-        ref = torch_conv(x, w, one, zero, mode, 0)
-        got = run_sw(native_lib, x, w, one, zero, mode, 0, None)
-        if not torch.equal(got, ref):
-            bad.append(((B, H, W, Cin, N, mode), int((got != ref).sum()), int((~torch.isfinite(got)).sum())))
-    assert not bad, "mismatches: %s" % (bad,)
-
-
 # ----------------------------------------------------------------- fused stem + block 0 (nn_kernels.cu stem_ds)
 @pytest.mark.parametrize("B,H,stride", [(2, 224, 1), (2, 224, 2), (3, 64, 1), (1, 32, 2)])
 def test_stem_ds_fused_kernel(native_lib, B, H, stride):
@@ -317,14 +272,3 @@ def test_stem_ds_fused_kernel(native_lib, B, H, stride):
     assert torch.isfinite(got).all(), "unwritten outputs: %d" % int((~torch.isfinite(got)).sum())
     err = (got - ref).abs().max().item()
     assert err <= 1e-4 * ref.abs().max().item(), "max err %.3g vs scale %.3g" % (err, ref.abs().max().item())
-
-
-@pytest.mark.parametrize("B,H,W,Cin,N,mode", SW_CASES)
-def test_conv3_sw_random_with_epilogue(native_lib, B, H, W, Cin, N, mode):
-    x, w, scale, bias = make_case(B, H, W, Cin, N, 43, mode)
-    res = torch.randn(B, N, H, W)
-    for relu, r in ((1, None), (0, res)):
-        ref = torch_conv(x, w, scale, bias, mode, relu, r)
-        got = run_sw(native_lib, x, w, scale, bias, mode, relu, r)
-        assert torch.isfinite(got).all()
-        assert (got - ref).abs().max().item() <= 3e-3 * ref.abs().max().item()

@@ -34,9 +34,9 @@ def test_umeyama_recovers_a_similarity():
         np.testing.assert_allclose(est, T, atol=1e-9)
 
 
-def test_crop_face_maps_the_landmark_square_to_the_crop():
+def test_landmark_box_transform_maps_the_landmark_square_to_the_crop():
     lm = np.array([[300.0, 200.0], [500.0, 260.0], [420.0, 420.0], [310.0, 400.0]])
-    t = crop.crop_face(np.zeros((720, 1280, 3), np.uint8), lm, scale=1.4, image_size=224)
+    t = crop.landmark_box_transform(lm, scale=1.4, image_size=224)
     np.testing.assert_allclose(t.params, warp_ref.crop_face_ref((720, 1280, 3), lm, 1.4, 224), atol=1e-12)
     size = int(((500 - 300) + (420 - 200)) / 2 * 1.4)
     cx, cy = 500 - 100.0, 420 - 110.0
@@ -95,7 +95,7 @@ def test_crop_to_tensor_matches_oracle(native_lib, H, W, lo):
         cx, cy = W * (0.3 + 0.2 * i), H * (0.4 + 0.1 * i)
         half = min(H, W) * (0.2 + 0.15 * i)                           # the last crop reaches outside the frame
         lm = np.array([[cx - half, cy - half], [cx + half, cy + half * 0.9], [cx, cy]])
-        tforms.append(crop.crop_face(frames[i], lm, scale=1.4, image_size=224))
+        tforms.append(crop.landmark_box_transform(lm, scale=1.4, image_size=224))
     tforms[1] = crop.SimilarityTransform(tforms[1].params @ _similarity(1.0, 0.35, 0.0, 0.0))   # a rotated crop as well
     got = crop.crop_to_tensor(torch.from_numpy(frames).to(DEV), tforms, 224).cpu().numpy()
     for i in range(B):

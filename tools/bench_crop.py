@@ -23,7 +23,7 @@ def main():
     tf = []
     for i in range(B):
         cx, cy, half = 960 + rng.uniform(-300, 300), 540 + rng.uniform(-150, 150), rng.uniform(120, 260)
-        tf.append(crop.crop_face(None, np.array([[cx - half, cy - half], [cx + half, cy + half]]), 1.4, 224))
+        tf.append(crop.landmark_box_transform(np.array([[cx - half, cy - half], [cx + half, cy + half]]), 1.4, 224))
     rendered = torch.rand(B, 3, 224, 224, device=dev)
 
     def timed(fn):
