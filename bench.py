@@ -1,25 +1,36 @@
 #!/usr/bin/env python
-"""bench.py — faces/sec of the SMIRK hot path (encode -> FLAME -> render @224^2) on N B200s.
+"""bench.py — faces/sec of the SMIRK hot path (encode -> FLAME -> render @224^2, and the full cycle with
+SmirkGenerator) on N B200s.
 
 Contract:
   python bench.py --gpus N --steps K --warmup W            product arm (under torchrun for N > 1)
   python bench.py --impl reference ...                     the reference's CPU path (oracle port) arm
 
-A step = one pass of the hot path over one batch of synthetic 224x224 RGB faces per GPU
-(BASELINE.json configs[1]: encoder+FLAME+raster, batch 32 per GPU; `--generator` switches to
-configs[2], the full cycle with SmirkGenerator; `--batch` changes the per-GPU batch).
-  value  : faces/s with the input batches already resident in HBM, CUDA-graph replay, timed with CUDA
-           events over exactly K steps between barriers, max over ranks.  Inputs rotate over a set of
-           batches larger than L2 so no step re-reads its input from cache.
-  e2e    : the same metric through SmirkPipeline.run_host(): pinned host images -> H2D -> graph ->
-           D2H of rendered image + vertices + FLAME parameters into pinned host memory, every step.
-  roofline: dominant kernel (largest share of device time) from the library's built-in event
-           profiler, live in this run: algorithmic bytes (or FLOPs) per launch / mean launch time.
-  cpu_baseline: the oracle port of the reference (torch CPU ops + C rasteriser) on the host cores.
+A step = one pass of the hot path over one batch of synthetic 224x224 RGB faces per GPU.  One run measures TWO
+workloads and prints ONE JSON line:
+  headline      BASELINE.json configs[1]: encoder + FLAME + raster, batch 32 per GPU (`--batch`);
+  `full_cycle`  BASELINE.json configs[2]/[4]: encoder -> FLAME -> raster -> SmirkGenerator, batch 256 per GPU
+                (`--full-batch`; `--no-full-cycle` skips it, `--generator` makes it the headline instead).
+For each workload:
+  value     faces/s with the input batches resident in HBM: CUDA-graph replay over `--slots` pipeline lanes, CUDA events
+            around exactly K steps, repeated over `--windows` back-to-back windows; the reported figure is the MEDIAN
+            window (min / max / relative spread alongside), max over ranks per window.  Inputs rotate over a set of
+            batches larger than L2.  For N > 1 the NCCL all-gather of the final outputs runs INSIDE the timed region
+            (on a communication stream, overlapping the next batch); `no_gather` repeats the measurement without it.
+  e2e       the same metric through SmirkPipeline.run_host(): pinned host images -> H2D -> graph -> D2H of rendered
+            image + vertices + FLAME parameters (+ reconstructed image) into pinned host memory, every step.
+  roofline  dominant kernel (largest share of device time) from the library's built-in event profiler, live in this
+            run: algorithmic bytes (or FLOPs) per launch / mean launch time; plus `in_situ`: step-level compulsory
+            bytes, measured DRAM traffic and FLOPs divided by the TIMED ms_per_step (what the mix achieves, not the
+            kernel alone).
+  parity    max errors of the timed configuration against the CPU oracle, checked in-run on one batch.
+  cpu_baseline: `bench.py --impl reference` run as a child process on the host cores (so both arms share one code path
+            and one thread-count choice).
 """
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import tempfile
@@ -31,14 +42,18 @@ sys.path.insert(0, ROOT)
 
 METRIC = "faces/sec encode->FLAME->render @224^2"
 UNIT = "faces/s"
+FLOPS_PER_FACE = {False: 0.941e9, True: 28.77e9}            # encoder+FLAME ; + generator
+COMPULSORY_BYTES_PER_FACE = {False: 1.328e6, True: 2.532e6}
+CONSTANT_BYTES = {False: 38.0e6, True: 163.5e6}             # weights / FLAME constants read once per step
 
 
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return dict(hbm=float(d["hbm_gbs"]), tensor=float(d.get("bf16_tflops", 1590.0)), source="measured")
-    return dict(hbm=6650.0, tensor=1590.0, source="fallback")
+        return dict(hbm=float(d["hbm_gbs"]), tensor=float(d.get("bf16_tflops", 1590.0)),
+                    tensor_sustained=float(d.get("bf16_tflops_sustained", 1400.0)), source="measured")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, source="fallback")
 
 
 class ClockSampler:
@@ -73,10 +88,10 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
             except Exception:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -84,27 +99,38 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload_name(generator, batch):
+    if generator:
+        return "configs[2]: full cycle encoder->FLAME->raster->smirk_generator 224x224, batch %d per GPU" % batch
+    return "configs[1]: encoder+FLAME+raster 224x224, batch %d per GPU" % batch
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_pass(root, sample, with_generator, threads=None):
+_CPU_STATE = {}
+
+
+def cpu_reference_pass(root, sample, with_generator, threads=None, seed=9001):
     """One pass of the reference's CPU path (oracle port) over `sample` faces; returns seconds."""
     import torch
     from smirk_b200 import synth_inputs
     from oracle import encoder_ref, flame_ref, render_ref, generator_ref
     if threads:
         torch.set_num_threads(threads)
-    st = cpu_reference_pass.state
-    if not st:
+    st = _CPU_STATE
+    if "enc_sd" not in st:
         import smirk_b200
         enc = smirk_b200.SmirkEncoder()
         st["enc_sd"] = synth_inputs.random_state_dict(enc.state_dict(), seed=7)
         st["fc"], st["rc"] = flame_ref.FlameConstants(root), render_ref.RenderConstants(root)
-        if with_generator:
-            gen = smirk_b200.SmirkGenerator(6, 3, 32, 5)
-            st["gen_sd"] = synth_inputs.random_state_dict(gen.state_dict(), seed=7)
-    img = synth_inputs.images(sample, 9001)
+    if with_generator and "gen_sd" not in st:
+        import smirk_b200
+        gen = smirk_b200.SmirkGenerator(6, 3, 32, 5)
+        st["gen_sd"] = synth_inputs.random_state_dict(gen.state_dict(), seed=7)
+    img = synth_inputs.images(sample, seed)
+    mask = synth_inputs.masked_images(sample, seed + 1) if with_generator else None
     t0 = time.perf_counter()
     with torch.no_grad():
         p = encoder_ref.encoder_forward_ref(st["enc_sd"], img)
@@ -113,77 +139,305 @@ def cpu_reference_pass(root, sample, with_generator, threads=None):
         ro = render_ref.render_forward_ref(st["rc"], fo["vertices"], p["cam"], landmarks_fan=fo["landmarks_fan"],
                                            landmarks_mp=fo["landmarks_mp"])
         if with_generator:
-            generator_ref.generator_forward_ref(st["gen_sd"], torch.cat([ro["rendered_img"], synth_inputs.masked_images(sample, 9002)], 1))
+            generator_ref.generator_forward_ref(st["gen_sd"], torch.cat([ro["rendered_img"], mask], 1))
     return time.perf_counter() - t0
 
 
-cpu_reference_pass.state = {}
-
-
 def pick_cpu_threads(root, with_generator):
-    """torch's intra-op pool is pathological at some thread counts on small-kernel workloads (SURVEY.md
-    §6: lbs() 1.4 ms at 1 thread vs 27 ms at 8).  Time a 2-face pass at a few thread counts and keep
-    the fastest, so the CPU arm gets the best configuration the host offers."""
+    """torch's intra-op pool is pathological at some thread counts on small-kernel workloads (lbs() 1.4 ms
+    at 1 thread vs 27 ms at 8).  Time a 4-face pass (best of two) at a few thread counts and keep the fastest; the
+    choice is cached per host so the product arm's cpu_baseline and the reference arm report the same configuration."""
     import torch
     n = os.cpu_count() or 1
-    cands = sorted({1, max(1, n // 4), max(1, n // 2), n, min(n, 16), min(n, 32)})
-    cpu_reference_pass(root, 1, with_generator, threads=1)                 # build state, warm caches
+    cache = os.path.join(tempfile.gettempdir(), "smk_cpu_threads_%d_%d.json" % (n, int(with_generator)))
+    try:
+        c = int(json.load(open(cache))["threads"])
+        if 1 <= c <= n:
+            torch.set_num_threads(c)
+            return c
+    except Exception:
+        pass
+    cands = sorted({max(1, n // 8), max(1, n // 4), max(1, n // 2), n, min(n, 16), min(n, 32)})
+    cpu_reference_pass(root, 1, with_generator, threads=cands[0])                 # build state, warm caches
     best = None
     for c in cands:
-        sec = cpu_reference_pass(root, 2, with_generator, threads=c)
+        sec = min(cpu_reference_pass(root, 4, with_generator, threads=c) for _ in range(2))
         if best is None or sec < best[1]:
             best = (c, sec)
     torch.set_num_threads(best[0])
+    try:
+        json.dump({"threads": best[0]}, open(cache, "w"))
+    except OSError:
+        pass
     return best[0]
 
 
-def run_reference_arm(args, root, rank, world):
-    """--impl reference: the reference's own CPU implementation (oracle port; the reference is pure
-    Python + third-party wheels and cannot travel to the GPU box).  Rank 0 only."""
+def run_reference_arm(args, root, rank):
+    """--impl reference: the reference's own CPU implementation (oracle port; the reference is pure Python + third-party
+    wheels that are not installable offline and cannot travel to the GPU box).  Rank 0 only.  K timed steps, each one
+    pass over a full batch of the same synthetic workload."""
     if rank != 0:
         return
     import torch
-    sample = args.cpu_sample
+    B = args.batch
     threads = pick_cpu_threads(root, args.generator)
-    cpu_reference_pass(root, sample, args.generator, threads=threads)
-    t = [cpu_reference_pass(root, sample, args.generator, threads=threads) for _ in range(max(1, min(args.steps, 5)))]
-    sec = sum(t) / len(t)
-    val = sample / sec
-    wl = workload_name(args)
+    W = max(1, min(args.warmup, 2))
+    for i in range(W):
+        cpu_reference_pass(root, B, args.generator, threads=threads, seed=8000 + i)
+    K = max(1, args.steps)
+    t = [cpu_reference_pass(root, B, args.generator, threads=threads, seed=9001 + 2 * i) for i in range(K)]
+    sec = statistics.median(t)
+    val = B / sec
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(t),
-        "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl, "faces_per_step": sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": "%d faces per step of the same synthetic workload (oracle port: torch CPU ops + C rasteriser)" % sample},
+        "config": {"workload": workload_name(args.generator, B), "global_batch": B, "faces_per_gpu_per_step": B,
+                   "image": "224x224 RGB fp32", "faces_per_step": B, "timing": "median of %d passes (min %.1f ms, max %.1f ms)" % (K, min(t) * 1e3, max(t) * 1e3)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "host_cpus": os.cpu_count(),
+                         "sample": "%d faces per step (one full batch of the same synthetic workload), %d steps; oracle port: torch CPU ops (oneDNN) + C rasteriser" % (B, K)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_name(args):
-    if args.generator:
-        return "configs[2]: full cycle encoder->FLAME->raster->smirk_generator 224x224, batch %d per GPU" % args.batch
-    return "configs[1]: encoder+FLAME+raster 224x224, batch %d per GPU" % args.batch
+def child_cpu_baseline(args, generator, batch, steps=3):
+    """Run the reference arm as a child process (full CPU affinity, its own torch thread pool) and return its
+    cpu_baseline object — the product arm and the reference arm thereby report the same baseline."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--gpus", "1", "--steps", str(steps), "--warmup", "1",
+           "--batch", str(batch)] + (["--generator"] if generator else [])
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        allcpus = set(range(os.cpu_count() or 1))
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env,
+                           preexec_fn=lambda: os.sched_setaffinity(0, allcpus))
+        for ln in reversed(r.stdout.splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"error": (r.stderr or "no output")[-300:]}
+    except Exception as e:                                    # the baseline is a report, never a reason to lose the GPU numbers
+        return {"error": repr(e)[:300]}
 
 
 # --------------------------------------------------------------------------------------- product arm
+PRECISIONS = {"fp32": 0, "tf32-unfused": 1, "tf32": 2, "tf32x3": 3}
+
+
+class Ctx:
+    pass
+
+
+def timed_windows(cx, step, join, K, W, R):
+    """W warm-up steps, then R back-to-back windows of exactly K steps, each bracketed by CUDA events on the current
+    stream (which joins every lane / copy / communication stream before the closing event); barrier + synchronize on
+    both sides.  Returns the per-window ms, max over ranks."""
+    import torch
+    for i in range(W):
+        step(i)
+    join()
+    cx.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(R)]
+    it = W
+    cx.barrier()
+    for r in range(R):
+        ev[r][0].record()
+        for _ in range(K):
+            step(it)
+            it += 1
+        join()
+        ev[r][1].record()
+    cx.barrier()
+    t = torch.tensor([a.elapsed_time(b) for a, b in ev], device=cx.dev, dtype=torch.float64)
+    if cx.dist is not None:
+        cx.dist.all_reduce(t, op=cx.dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+def window_stats(ms, K):
+    med = statistics.median(ms)
+    return {"n": len(ms), "steps_per_window": K, "median_ms": med, "min_ms": min(ms), "max_ms": max(ms),
+            "rel_spread": (max(ms) - min(ms)) / med if med > 0 else None}
+
+
+def run_workload(cx, args, B, generator, slots, R, with_cpu):
+    """Measure one workload (device-resident, e2e, ± gather for N > 1, kernel breakdown, parity).  Returns a dict."""
+    import torch
+    import smirk_b200
+    from smirk_b200 import _lib, synth_inputs
+    from smirk_b200.pipeline import SmirkPipeline
+    dev, world, rank = cx.dev, cx.world, cx.rank
+    K, W = args.steps, max(args.warmup, 3)
+    enc = smirk_b200.SmirkEncoder()
+    enc.load_state_dict(synth_inputs.random_state_dict(enc.state_dict(), seed=7))
+    enc = enc.eval().to(dev)
+    enc.precision = PRECISIONS[args.precision]
+    gen = None
+    if generator:
+        gen = smirk_b200.SmirkGenerator(6, 3, 32, 5)
+        gen.load_state_dict(synth_inputs.random_state_dict(gen.state_dict(), seed=7))
+        gen = gen.eval().to(dev)
+        gen.precision = 0 if args.precision == "fp32" else 1
+    fl, rd = smirk_b200.FLAME().to(dev), smirk_b200.Renderer().to(dev)
+    pipe = SmirkPipeline(enc, fl, rd, gen, device=dev, slots=slots)
+
+    # rotating input set larger than L2 (126 MB): Rset batches of B x 602 KB (x2 with the masked image)
+    per = B * 3 * 224 * 224 * 4 * (2 if generator else 1)
+    Rset = max(2, -(-160_000_000 // per))
+    host_imgs = [synth_inputs.images(B, 5000 + rank * 100 + i).pin_memory() for i in range(Rset)]
+    host_masks = [synth_inputs.masked_images(B, 6000 + rank * 100 + i).pin_memory() for i in range(Rset)] if generator else None
+    dev_imgs = [h.to(dev) for h in host_imgs]
+    dev_masks = [h.to(dev) for h in host_masks] if generator else None
+    rec = pipe.capture(B)
+    for lane in range(1, pipe.slots):
+        pipe.capture(B, lane)
+    keys = ("rendered_img", "vertices", "params") + (("reconstructed_img",) if generator else ())
+
+    def dev_step(i):            # batch i goes to lane i % slots (own stream + graph replica): consecutive batches overlap
+        pipe.submit(i, dev_imgs[i % Rset], dev_masks[i % Rset] if generator else None)
+
+    def host_step(i):
+        cx.last = pipe.run_host(host_imgs[i % Rset], i, host_masks[i % Rset] if generator else None, keys)
+
+    out = {"batch": B, "launches_per_step": int(rec["launches"])}
+    faces = B * world * K
+    gather_keys = pipe.enable_gather(keys) if (world > 1 and not args.no_gather) else ()
+    sampler = ClockSampler(cx.local)
+    if rank == 0:
+        sampler.start()
+    ms = timed_windows(cx, dev_step, pipe.join, K, W, R)
+    out["clocks"] = sampler.stop() if rank == 0 else None
+    out["windows"] = window_stats(ms, K)
+    out["ms_per_step"] = out["windows"]["median_ms"] / K
+    out["value"] = faces / (out["windows"]["median_ms"] / 1e3)
+    h2d, d2h = pipe.bytes_per_step(B, keys)
+    ms2 = timed_windows(cx, host_step, pipe.join, K, W, max(3, R // 2))
+    out["e2e"] = {"value": faces / (statistics.median(ms2) / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                  "ms_per_step": statistics.median(ms2) / K, "windows": window_stats(ms2, K),
+                  "api": "SmirkPipeline.run_host (pinned host in/out, %d lanes, copies on their own streams)" % pipe.slots,
+                  "host_checksum": float(cx.last["params"].double().abs().sum())}          # touches the host result
+    if gather_keys:
+        gb = pipe.gather_bytes_per_step(B)
+        out["gather"] = {"collective": "NCCL all_gather_into_tensor of %s per step, on a communication stream inside the timed region" % "+".join(gather_keys),
+                         "recv_bytes_per_rank_per_step": gb, "recv_gbs_per_rank": gb / (out["ms_per_step"] * 1e-3) / 1e9}
+        pipe.enable_gather(())
+        ms3 = timed_windows(cx, dev_step, pipe.join, K, W, max(3, R // 2))
+        ms4 = timed_windows(cx, host_step, pipe.join, K, W, max(3, R // 2))
+        out["no_gather"] = {"value": faces / (statistics.median(ms3) / 1e3), "ms_per_step": statistics.median(ms3) / K,
+                            "e2e_value": faces / (statistics.median(ms4) / 1e3)}
+
+    if rank != 0:
+        return out
+    # ---- per-kernel breakdown (eager, event-bracketed launches) ----
+    L = _lib.lib()
+    for i in range(2):
+        pipe.forward(dev_imgs[i % Rset], dev_masks[i % Rset] if generator else None)
+    torch.cuda.synchronize(dev)
+    L.smk_profiler_reset(); L.smk_profiler_enable(1)
+    NP = 5 if B <= 64 else 2
+    for i in range(NP):
+        pipe.forward(dev_imgs[(i + 3) % Rset], dev_masks[(i + 3) % Rset] if generator else None)
+    torch.cuda.synchronize(dev)
+    breakdown = _lib.profiler_report()
+    L.smk_profiler_enable(0); L.smk_profiler_reset()
+    peaks = cx.peaks
+    tot = sum(v["ms"] for v in breakdown.values())
+    for v in breakdown.values():
+        v["share"] = v["ms"] / tot
+        v["ms_per_launch"] = v["ms"] / v["launches"]
+        v["gbs"] = v["bytes"] / v["ms"] / 1e6
+        v["tflops"] = v["flops"] / v["ms"] / 1e9
+    top_tag, top = max(breakdown.items(), key=lambda kv: kv[1]["ms"])
+    # Every tensor-core kernel here computes in TF32: its ceiling is HALF the measured bf16 GEMM peak (tcgen05 kind::tf32
+    # runs at half the kind::f16 rate), and the hbm/tensor ridge is judged against that.
+    tf32_peak = peaks["tensor"] / 2.0
+    ai = top["flops"] / max(top["bytes"], 1.0)
+    ridge = tf32_peak * 1e3 / peaks["hbm"]
+    if "tc" in top_tag and ai > ridge:
+        roof = {"bound": "tensor", "achieved": top["tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
+                "peak_note": "TF32 = measured bf16 cuBLAS peak / 2"}
+    else:
+        roof = {"bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s"}
+    traffic, step_traffic = None, None
+    tname = "r02_ncu_dram_traffic_%s_b%d_%s.json" % ("c3" if generator else "c2", B, args.precision)
+    tpath = os.path.join(ROOT, "profiles", tname)
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        tk = tj.get("kernels", {}).get(top_tag.split(":")[0])
+        traffic = tk["traffic_bytes_per_launch"] if tk else None
+        step_traffic = tj.get("step_traffic_bytes")
+    roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, kernel=top_tag, share_of_step=top["share"],
+                launches_per_step=top["launches"] / NP, us_per_launch=top["ms_per_launch"] * 1e3, peak_source=peaks["source"],
+                arithmetic_intensity=ai, ridge_flop_per_byte=ridge,
+                algorithmic_bytes_per_launch=top["bytes"] / top["launches"], algorithmic_flops_per_launch=top["flops"] / top["launches"])
+    # in-situ: what the TIMED pipeline (all lanes and streams overlapping) achieves per GPU
+    sec = out["ms_per_step"] * 1e-3
+    comp = COMPULSORY_BYTES_PER_FACE[generator] * B + CONSTANT_BYTES[generator]
+    roof["in_situ"] = {
+        "ms_per_step": out["ms_per_step"],
+        "compulsory_bytes_per_step": comp, "hbm_frac_compulsory": comp / sec / 1e9 / peaks["hbm"],
+        "dram_traffic_bytes_per_step": step_traffic,
+        "hbm_frac_traffic": (step_traffic / sec / 1e9 / peaks["hbm"]) if step_traffic else None,
+        "tflops": FLOPS_PER_FACE[generator] * B / sec / 1e12,
+        "tensor_frac_tf32": FLOPS_PER_FACE[generator] * B / sec / 1e12 / tf32_peak,
+        "tensor_frac_tf32_sustained": FLOPS_PER_FACE[generator] * B / sec / 1e12 / (peaks["tensor_sustained"] / 2.0),
+        "eager_serial_ms_per_step": tot / NP,
+    }
+    out["roofline"] = roof
+    out["kernel_shares"] = {k: round(v["share"], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])[:8]}
+    if args.profile_out:
+        suffix = "_c3" if generator else "_c2"
+        with open(args.profile_out.replace(".json", suffix + ".json"), "w") as fh:
+            json.dump({"batch": B, "steps_profiled": NP, "eager_ms_per_step": tot / NP, "kernels": breakdown}, fh, indent=1)
+
+    # ---- parity of the timed configuration, in-run on one batch (the oracle is the checker only) ----
+    if not args.no_parity:
+        try:
+            from oracle import parity_check
+            nb = min(B, 32)
+            img = synth_inputs.images(nb, 5000)
+            p = enc(img.to(dev))
+            fo = fl.forward(p)
+            ro = rd.render_full(fo["vertices"], p["cam"])
+            rep = parity_check.pipeline_report(cx.root, enc.state_dict(), img,
+                                               {"params_dict": p, "vertices": fo["vertices"], "rendered_img": ro["rendered_img"],
+                                                "transformed_vertices": ro["transformed_vertices"], "pix_to_face": ro["pix_to_face"]})
+            rep["checked_against"] = "CPU oracle (oracle/: torch fp32 restatement + C rasteriser), %d faces of the timed workload" % nb
+            rep["north_star"] = {"vertices_rel<=1e-4": rep["vertices_rel"] <= 1e-4, "pixels_stage_abs<=1.7e-4": rep["pixels_stage_abs"] <= 1.7e-4,
+                                 "p2f_stage_bit_exact": rep.get("p2f_stage_mismatch") == 0}
+            out["parity"] = rep
+        except Exception as e:
+            out["parity"] = {"error": repr(e)[:300]}
+    if with_cpu:
+        out["cpu_baseline"] = child_cpu_baseline(args, generator, min(B, 32), steps=3)
+    del pipe
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="smirk_b200", choices=["smirk_b200", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="faces per GPU per step (configs[1] = 32)")
-    ap.add_argument("--generator", action="store_true", help="include SmirkGenerator (configs[2], full cycle)")
-    ap.add_argument("--cpu-sample", type=int, default=16, help="faces per CPU-baseline pass")
+    ap.add_argument("--batch", type=int, default=32, help="faces per GPU per step of the headline workload (configs[1] = 32)")
+    ap.add_argument("--full-batch", type=int, default=256, help="faces per GPU per step of the full-cycle workload (configs[2]/[4] = 256)")
+    ap.add_argument("--generator", action="store_true", help="make the full cycle (with SmirkGenerator) the headline workload at --batch")
+    ap.add_argument("--no-full-cycle", action="store_true", help="skip the extra full_cycle block")
+    ap.add_argument("--windows", type=int, default=21, help="back-to-back repeats of the K-step timed window (median reported)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: leave the NCCL all-gather of the outputs out of the timed region")
+    ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--slots", type=int, default=4, help="pipeline lanes: consecutive batches alternate over this many stream/graph replicas")
-    ap.add_argument("--profile-out", default=None, help="write the per-kernel breakdown JSON here")
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "tf32-unfused"],
-                    help="tf32: 1x1/3x3/transposed convs on tcgen05 tensor cores (the reference's own cuDNN default); "
-                         "fp32: every conv on the exact fp32 CUDA-core path")
+    ap.add_argument("--full-slots", type=int, default=2)
+    ap.add_argument("--profile-out", default=None, help="write the per-kernel breakdown JSON here (suffix _c2 / _c3 added)")
+    ap.add_argument("--precision", default="tf32x3", choices=sorted(PRECISIONS),
+                    help="encoder arithmetic.  tf32x3: tcgen05 tensor cores with error-compensated 3xTF32 products (fp32-equivalent; "
+                         "the parity path and the default); tf32: plain TF32 tensor cores (the reference's cuDNN default); "
+                         "fp32: exact fp32 CUDA cores.  The generator runs TF32 tcgen05 unless fp32 is chosen.")
     args = ap.parse_args()
     if args.profile_out:
         args.profile_out = os.path.abspath(args.profile_out)
@@ -196,177 +450,72 @@ def main():
     os.chdir(root)
 
     if args.impl == "reference":
-        run_reference_arm(args, root, rank, world)
+        run_reference_arm(args, root, rank)
         return
 
+    affinity = None
+    if not args.no_affinity:
+        from smirk_b200 import affinity as aff
+        affinity = aff.pin_to_gpu(local)                       # before torch allocates any pinned memory
     import torch
-    import smirk_b200
-    from smirk_b200 import _lib, synth_inputs
-    from smirk_b200.pipeline import SmirkPipeline
     assert torch.cuda.is_available(), "bench.py (product arm) needs a GPU; there is no CPU fallback"
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
+    cx = Ctx()
+    cx.dev, cx.rank, cx.world, cx.local, cx.root, cx.peaks, cx.last = torch.device("cuda", local), rank, world, local, root, load_peaks(), None
+    cx.dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=cx.dev)
+        cx.dist = dist
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
 
     def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+        if cx.dist is not None:
+            cx.dist.barrier()
+        torch.cuda.synchronize(cx.dev)
+    cx.barrier = barrier
 
-    B, K, W = args.batch, args.steps, max(args.warmup, 3)
-    enc = smirk_b200.SmirkEncoder()
-    enc.load_state_dict(synth_inputs.random_state_dict(enc.state_dict(), seed=7))
-    enc = enc.eval().to(dev)
-    # tf32 = tensor-core convs + fused expand/depthwise blocks in the encoder; tf32-unfused keeps one kernel per layer
-    enc.precision = {"fp32": 0, "tf32-unfused": 1, "tf32": 2}[args.precision]
-    gen = None
-    if args.generator:
-        gen = smirk_b200.SmirkGenerator(6, 3, 32, 5)
-        gen.load_state_dict(synth_inputs.random_state_dict(gen.state_dict(), seed=7))
-        gen = gen.eval().to(dev)
-        gen.precision = min(enc.precision, 1)
-    pipe = SmirkPipeline(enc, smirk_b200.FLAME().to(dev), smirk_b200.Renderer().to(dev), gen, device=dev, slots=args.slots)
-
-    # rotating input set larger than L2 (126 MB): R batches of B x 602 KB
-    per = B * 3 * 224 * 224 * 4 * (2 if gen is not None else 1)
-    R = max(2, -(-160_000_000 // per))
-    host_imgs = [synth_inputs.images(B, 5000 + rank * 100 + i).pin_memory() for i in range(R)]
-    host_masks = [synth_inputs.masked_images(B, 6000 + rank * 100 + i).pin_memory() for i in range(R)] if gen is not None else None
-    dev_imgs = [h.to(dev) for h in host_imgs]
-    dev_masks = [h.to(dev) for h in host_masks] if gen is not None else None
-    rec = pipe.capture(B)
-    for lane in range(1, pipe.slots):
-        pipe.capture(B, lane)
-
-    def dev_step(i):
-        # batch i goes to lane i % slots (own stream + graph replica): consecutive batches overlap
-        pipe.submit(i, dev_imgs[i % R], dev_masks[i % R] if gen is not None else None)
-
-    # ---- device-resident throughput (value) ----
-    for i in range(W):
-        dev_step(i)
-    pipe.join()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_before = _lib.lib().smk_launch_count()
-    barrier()
-    e0.record()
-    for i in range(K):
-        dev_step(W + i)
-    pipe.join()                                  # the timing stream waits for every lane
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-
-    # ---- end to end through the public host API (e2e) ----
-    keys = ("rendered_img", "vertices", "params") + (("reconstructed_img",) if gen is not None else ())
-    h2d, d2h = pipe.bytes_per_step(B, keys)
-    for i in range(W):
-        pipe.run_host(host_imgs[i % R], i, host_masks[i % R] if gen is not None else None, keys)
-    pipe.join()
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    last = None
-    for i in range(K):
-        last = pipe.run_host(host_imgs[(W + i) % R], W + i, host_masks[(W + i) % R] if gen is not None else None, keys)
-    pipe.join()                                  # includes the copy streams: every D2H has landed
-    e3.record()
-    barrier()
-    t2 = torch.tensor([e2.elapsed_time(e3)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t2.item())
-    checksum = float(last["params"].double().abs().sum())                       # touch the host result
-
-    # ---- per-kernel breakdown (eager, event-bracketed launches; rank 0) ----
-    breakdown, roof = None, None
-    if rank == 0:
-        L = _lib.lib()
-        for i in range(2):
-            pipe.forward(dev_imgs[i % R], dev_masks[i % R] if gen is not None else None)
-        torch.cuda.synchronize(dev)
-        L.smk_profiler_reset(); L.smk_profiler_enable(1)
-        NP = 5
-        for i in range(NP):
-            pipe.forward(dev_imgs[(i + 3) % R], dev_masks[(i + 3) % R] if gen is not None else None)
-        torch.cuda.synchronize(dev)
-        breakdown = _lib.profiler_report()
-        L.smk_profiler_enable(0); L.smk_profiler_reset()
-        peaks = load_peaks()
-        tot = sum(v["ms"] for v in breakdown.values())
-        for v in breakdown.values():
-            v["share"] = v["ms"] / tot
-            v["ms_per_launch"] = v["ms"] / v["launches"]
-            v["gbs"] = v["bytes"] / v["ms"] / 1e6
-            v["tflops"] = v["flops"] / v["ms"] / 1e9
-        top_tag, top = max(breakdown.items(), key=lambda kv: kv[1]["ms"])
-        ai = top["flops"] / max(top["bytes"], 1.0)
-        ridge = peaks["tensor"] * 1e3 / peaks["hbm"]
-        if "tc" in top_tag and ai > ridge:
-            roof = {"bound": "tensor", "achieved": top["tflops"], "peak": peaks["tensor"], "unit": "TFLOP/s"}
-        else:
-            roof = {"bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s"}
-        # DRAM traffic per launch of that kernel from the committed ncu capture of this same workload
-        # (profiles/*ncu_dram_traffic*.json: dram__bytes_read.sum + dram__bytes_write.sum); null if the
-        # capture does not cover this configuration.
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_ncu_dram_traffic_c2_b32_%s.json" % args.precision)
-        if os.path.exists(tpath) and B == 32 and gen is None:
-            tk = json.load(open(tpath)).get("kernels", {}).get(top_tag.split(":")[0])
-            if tk:
-                traffic = tk["traffic_bytes_per_launch"]
-        roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, kernel=top_tag, share_of_step=top["share"],
-                    launches_per_step=top["launches"] / NP, us_per_launch=top["ms_per_launch"] * 1e3,
-                    peak_source=peaks["source"],
-                    algorithmic_bytes_per_launch=top["bytes"] / top["launches"],
-                    algorithmic_flops_per_launch=top["flops"] / top["launches"])
-        if args.profile_out:
-            with open(args.profile_out, "w") as fh:
-                json.dump({"batch": B, "steps_profiled": NP, "eager_ms_per_step": tot / NP, "kernels": breakdown}, fh, indent=1)
-
-    # ---- CPU baseline beside it (rank 0, N = 1 only) ----
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        import torch as _t
-        threads = pick_cpu_threads(root, args.generator)                 # also warms up (weights, C oracle)
-        sec = cpu_reference_pass(root, args.cpu_sample, args.generator, threads=threads)
-        cpu = {"value": args.cpu_sample / sec, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
-               "sample": "%d faces, one pass of the same workload (oracle port: torch CPU ops + C rasteriser), %.1f s" % (args.cpu_sample, sec)}
+    head = run_workload(cx, args, args.batch, args.generator, args.slots, max(1, args.windows), with_cpu=(world == 1 and not args.no_cpu_baseline))
+    full = None
+    if not args.generator and not args.no_full_cycle:
+        full = run_workload(cx, args, args.full_batch, True, args.full_slots, max(1, min(args.windows, 5)), with_cpu=False)
 
     if rank == 0:
-        faces = B * world * K
+        B, K = args.batch, args.steps
         line = {
-            "metric": METRIC, "value": faces / (ms_total / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 convs (fp32 accumulate), f32 elsewhere" if args.precision != "fp32" else "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "precision": args.precision, "global_batch": B * world, "faces_per_gpu_per_step": B,
-                       "image": "224x224 RGB fp32", "parallelism": "frame-shard dp%d" % world,
-                       "l2_policy": "inputs rotate over %d batches (%.0f MB > 126 MB L2)" % (R, R * per / 1e6),
-                       "execution": "CUDA graph replay, %d kernels per step, %d-lane software pipeline over consecutive steps" % (rec["launches"], pipe.slots)},
-            "e2e": {"value": faces / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / K, "api": "SmirkPipeline.run_host (pinned host in/out, %d lanes, copies on a second stream)" % pipe.slots,
-                    "host_checksum": checksum},
-            "gpu_launches": int(rec["launches"]) * K,
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"tf32x3": "tf32x3 (tcgen05 TF32 products, 3-term error-compensated = fp32-equivalent; fp32 accumulate), f32 elsewhere",
+                      "tf32": "tf32 convs (fp32 accumulate), f32 elsewhere", "tf32-unfused": "tf32 convs (fp32 accumulate), f32 elsewhere",
+                      "fp32": "f32"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.generator, B), "precision": args.precision, "global_batch": B * world,
+                       "faces_per_gpu_per_step": B, "image": "224x224 RGB fp32", "parallelism": "frame-shard dp%d" % world,
+                       "l2_policy": "inputs rotate over a set of batches > 126 MB L2 (160 MB)",
+                       "timing": "median of %d back-to-back windows of exactly %d steps (CUDA events, max over ranks per window)" % (head["windows"]["n"], K),
+                       "execution": "CUDA graph replay, %d kernels per step, %d-lane software pipeline over consecutive steps" % (head["launches_per_step"], args.slots),
+                       "host_affinity": affinity},
+            "windows": head["windows"],
+            "e2e": head["e2e"],
+            "gpu_launches": head["launches_per_step"] * K,
+            "clocks": head["clocks"], "roofline": head.get("roofline"), "cpu_baseline": head.get("cpu_baseline"),
+            "parity": head.get("parity"), "kernel_shares": head.get("kernel_shares"),
         }
-        if breakdown:
-            line["kernel_shares"] = {k: round(v["share"], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])[:8]}
+        for k in ("gather", "no_gather"):
+            if k in head:
+                line[k] = head[k]
+        if full is not None:
+            fc = {"workload": workload_name(True, args.full_batch), "value": full["value"], "unit": UNIT, "ms_per_step": full["ms_per_step"],
+                  "global_batch": args.full_batch * world, "windows": full["windows"], "e2e": full["e2e"],
+                  "gpu_launches": full["launches_per_step"] * K, "lanes": args.full_slots, "generator_dtype": "tf32 (fp32 accumulate)",
+                  "roofline": full.get("roofline"), "kernel_shares": full.get("kernel_shares"), "clocks": full["clocks"], "parity": full.get("parity")}
+            for k in ("gather", "no_gather"):
+                if k in full:
+                    fc[k] = full[k]
+            line["full_cycle"] = fc
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    if cx.dist is not None:
+        cx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -123,7 +123,9 @@ typedef struct {
     int n_shape;               /* 300 */
     int n_exp;                 /* 50 */
     int precision;             /* 0 = fp32 CUDA-core GEMMs, 1 = TF32 tcgen05 GEMMs for the 1x1 convs,
-                                  2 = 1 + inverted-residual blocks run expand-1x1 + depthwise-3x3 as one fused kernel */
+                                  2 = 1 + inverted-residual blocks run expand-1x1 + depthwise-3x3 as one fused kernel,
+                                  3 = 2 with error-compensated "3xTF32" tensor-core arithmetic (operands split into TF32
+                                      head + tail, three products per term): fp32-equivalent results, the parity path */
 } SmkEncoderDesc;
 
 int smk_encoder_create(const SmkEncoderDesc* desc, SmkEncoder** out);
@@ -214,6 +216,15 @@ int smk_debug_reflect_halo(float* buf, int B, int H, int W, int C, void* stream)
 int smk_debug_xdw(const float* x, int B, int H, int W, int Cin, const float* w1t, const float* scale1, const float* bias1,
                   int mid, const float* wdw, const float* scale2, const float* bias2, int stride, int round_out,
                   float* out, void* stream);
+
+/*   smk_debug_gemm_tc3x / smk_debug_xdw3x: the error-compensated 3xTF32 variants of the two tensor-core encoder kernels
+ *                  (encoder precision 3).  wt_hi / wt_lo (w1t_hi / w1t_lo) are the TF32 heads and tails of the weights:
+ *                  hi = tf32(w), lo = tf32(w - hi).  in is [M, ld_in] row-major; out [M, ld_out].                       */
+int smk_debug_gemm_tc3x(const float* in, int ld_in, int M, const float* wt_hi, const float* wt_lo, const float* scale,
+                        const float* bias, int N, int K, int relu, const float* res, int ld_res, float* out, int ld_out, void* stream);
+int smk_debug_xdw3x(const float* x, int B, int H, int W, int Cin, const float* w1t_hi, const float* w1t_lo, const float* scale1,
+                    const float* bias1, int mid, const float* wdw, const float* scale2, const float* bias2, int stride,
+                    float* out, void* stream);
 
 /*   smk_debug_stem_ds: fused stem conv (3x3 s2, 3 -> 16) + BN + ReLU + depthwise-separable block 0 (fp32 CUDA cores).
  *                      img [B,3,H,W] NCHW; stem_w [27][16] (k = (c*3+ky)*3+kx); dw_w [9][16]; pw_w [16 ci][16 co];

@@ -51,7 +51,7 @@ SYMBOLS = ["smk_version", "smk_last_error", "smk_launch_count", "smk_profiler_en
            "smk_project_points",
            "smk_encoder_create", "smk_encoder_destroy", "smk_encoder_workspace_bytes", "smk_encoder_forward",
            "smk_generator_create", "smk_generator_destroy", "smk_generator_workspace_bytes", "smk_generator_forward",
-           "smk_debug_conv_f32", "smk_debug_conv_tc", "smk_debug_reflect_halo", "smk_debug_xdw", "smk_debug_stem_ds",
+           "smk_debug_conv_f32", "smk_debug_conv_tc", "smk_debug_reflect_halo", "smk_debug_xdw", "smk_debug_stem_ds", "smk_debug_gemm_tc3x", "smk_debug_xdw3x",
            "smk_warp_workspace_bytes", "smk_crop_warp", "smk_warp_u8", "smk_f32chw_to_u8hwc",
            "smk_masking_create", "smk_masking_destroy", "smk_masking_workspace_bytes", "smk_masking_face_weights",
            "smk_masking_points", "smk_masking_compose"]
@@ -106,6 +106,8 @@ def lib():
     L.smk_masking_face_weights.argtypes = [vp, vp, vp, i, vp, vp, sz, vp]
     L.smk_masking_points.argtypes = [vp, vp, vp, vp, i, i, i, vp, vp]
     L.smk_masking_compose.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, i, i, i, vp, vp, sz, vp]
+    L.smk_debug_gemm_tc3x.argtypes = [vp, i, i, vp, vp, vp, vp, i, i, i, vp, i, vp, i, vp]
+    L.smk_debug_xdw3x.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp]
     L.smk_warp_workspace_bytes.argtypes = [i]
     L.smk_warp_workspace_bytes.restype = C.c_size_t
     L.smk_crop_warp.argtypes = [vp, i, i, i, vp, i, i, vp, vp, C.c_size_t, vp]
@@ -157,8 +159,29 @@ def stream_ptr(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class NativeHandle:
+    """Owner of one ``Smk*`` handle.  Passed to the C ABI like a ``c_void_p`` (``_as_parameter_``); the native
+    object is destroyed when the last Python reference goes away.  Modules drop their reference when their weights
+    change; a captured CUDA graph (``SmirkPipeline.capture``) keeps its own, so the packed weights a graph points
+    at outlive the module's re-pack."""
+
+    def __init__(self, ptr, destroy_name):
+        self._as_parameter_ = ptr
+        self._destroy_name = destroy_name
+
+    def __del__(self):
+        try:
+            if self._as_parameter_ is not None and _lib is not None:
+                getattr(_lib, self._destroy_name)(self._as_parameter_)
+        except Exception:
+            pass
+        self._as_parameter_ = None
+
+
 class Workspace:
-    """Per-module scratch owned by the PyTorch caching allocator, grown on demand."""
+    """Per-module scratch owned by the PyTorch caching allocator, grown on demand.  ``get`` never frees the previous
+    buffer itself: it only drops this object's reference, so anything that still holds the old tensor (a captured
+    CUDA graph's keep-alive list) keeps the memory."""
 
     def __init__(self):
         self.buf = None
@@ -167,6 +190,15 @@ class Workspace:
         if self.buf is None or self.buf.device != device or self.buf.numel() < nbytes:
             self.buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         return self.buf
+
+
+def buffers_signature(module, device, *extra):
+    """Cheap change detector for a module's parameters / buffers: versions + storage pointers."""
+    s = [str(device)] + list(extra)
+    for t in list(module.parameters()) + list(module.buffers()):
+        s.append(t._version)
+        s.append(t.data_ptr())
+    return tuple(s)
 
 
 def profiler_report():

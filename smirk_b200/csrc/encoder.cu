@@ -17,7 +17,7 @@ using smk::ConvProblem;
 
 constexpr float kBnEps = 1e-3f;
 
-struct ConvW { float* w = nullptr; float* wt = nullptr; float* scale = nullptr; float* bias = nullptr; int cin = 0, cout = 0; };   // w: [K][N] fp32 path, wt: [N][K] tcgen05 path
+struct ConvW { float* w = nullptr; float* wt = nullptr; float* wt_lo = nullptr; float* scale = nullptr; float* bias = nullptr; int cin = 0, cout = 0; };   // w: [K][N] fp32 path, wt: [N][K] tcgen05 path (TF32 heads), wt_lo: TF32 tails (3xTF32 path)
 enum Kind { DS = 0, IR = 1, CN = 2 };
 struct BlockDef { Kind kind; int stride; float exp; int cout; };
 struct Block { Kind kind; int stride, cin, mid, cout; bool skip; ConvW pw, dw, pwl; ConvW pw_f32; };   // pw_f32: fp32 [K][N] copy of a DS block's 1x1 (fused stem path)
@@ -60,14 +60,18 @@ struct TensorCursor {
 };
 
 // kind: 0 = 1x1 [Cout,Cin,1,1] -> W[Cin][Cout]; 1 = depthwise [C,1,3,3] -> W[9][C]; 2 = stem [16,3,3,3] -> W[27][16]
-bool fold_conv(TensorCursor& cur, int kind, int cin, int cout, bool tc, smk::DeviceArena& arena, ConvW* out, cudaError_t* err) {
+bool fold_conv(TensorCursor& cur, int kind, int cin, int cout, bool tc, smk::DeviceArena& arena, ConvW* out, cudaError_t* err, bool x3 = false) {
     const float* w = cur.next(); const float* g = cur.next(); const float* b = cur.next();
     const float* mu = cur.next(); const float* var = cur.next();
     if (!w || !g || !b || !mu || !var) return false;
-    std::vector<float> W, S(cout), Bi(cout);
+    std::vector<float> W, Wlo, S(cout), Bi(cout);
     if (kind == 0 && tc) {
         W.resize((size_t)cin * cout);                        // torch layout [Cout][Cin] is already [N][K]
         for (size_t i = 0; i < W.size(); ++i) W[i] = smk::round_tf32_host(w[i]);
+        if (x3) {                                            // w = head + tail exactly; the tail is itself a TF32 number up to 2^-22 |w|
+            Wlo.resize(W.size());
+            for (size_t i = 0; i < W.size(); ++i) Wlo[i] = smk::round_tf32_host(w[i] - W[i]);
+        }
     } else if (kind == 0) {
         W.resize((size_t)cin * cout);
         for (int o = 0; o < cout; ++o) for (int c = 0; c < cin; ++c) W[(size_t)c * cout + o] = w[(size_t)o * cin + c];
@@ -84,6 +88,7 @@ bool fold_conv(TensorCursor& cur, int kind, int cin, int cout, bool tc, smk::Dev
     }
     out->cin = cin; out->cout = cout;
     cudaError_t e = arena.upload(W, (kind == 0 && tc) ? &out->wt : &out->w);
+    if (e == cudaSuccess && !Wlo.empty()) e = arena.upload(Wlo, &out->wt_lo);
     if (e == cudaSuccess) e = arena.upload(S, &out->scale);
     if (e == cudaSuccess) e = arena.upload(Bi, &out->bias);
     *err = e;
@@ -96,30 +101,43 @@ struct SmkEncoder {
     Backbone bb[3];
     int n_shape = 300, n_exp = 50, precision = 0;
     size_t max_act = 0;          // floats per image of the largest activation
-    bool fuse_xdw = false;       // precision 2: inverted-residual blocks use the fused expand+depthwise kernel
+    bool fuse_xdw = false;       // precision >= 2: inverted-residual blocks use the fused expand+depthwise kernel
+    bool x3 = false;             // precision 3: 3xTF32 error-compensated tensor-core arithmetic (fp32-equivalent), no TF32 rounding of activations
+    bool present[3] = {false, false, false};   // a handle may hold a subset of the backbones (PoseEncoder / ShapeEncoder / ExpressionEncoder alone)
     smk::DeviceArena arena;
-    cudaStream_t side[2] = {nullptr, nullptr};     // fork/join streams for the two large backbones
-    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    // Fork/join plumbing for running the backbones as parallel branches of the caller's stream.  A forward takes the
+    // next set of a small pool (atomic round-robin), so up to kForkSets forwards of one handle may be in flight on
+    // different streams (with distinct workspaces) without sharing an event or a side stream: the handle is re-entrant.
+    static constexpr int kForkSets = 8;
+    struct ForkSet { cudaStream_t side[2] = {nullptr, nullptr}; cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr}; };
+    ForkSet forks[kForkSets];
+    mutable unsigned next_fork = 0;
     ~SmkEncoder() {
-        for (int s = 0; s < 2; ++s) { if (side[s]) cudaStreamDestroy(side[s]); if (join[s]) cudaEventDestroy(join[s]); }
-        if (fork) cudaEventDestroy(fork);
+        for (auto& f : forks) {
+            for (int s = 0; s < 2; ++s) { if (f.side[s]) cudaStreamDestroy(f.side[s]); if (f.join[s]) cudaEventDestroy(f.join[s]); }
+            if (f.fork) cudaEventDestroy(f.fork);
+        }
     }
 };
 
 extern "C" int smk_encoder_create(const SmkEncoderDesc* desc, SmkEncoder** out) {
     SMK_REQUIRE(desc && out, "smk_encoder_create: null argument");
-    SMK_REQUIRE(desc->precision >= 0 && desc->precision <= 2,
-                "smk_encoder_create: precision must be 0 (fp32), 1 (tf32 tcgen05 1x1 convs) or 2 (1 + fused expand/depthwise blocks)");
+    SMK_REQUIRE(desc->precision >= 0 && desc->precision <= 3,
+                "smk_encoder_create: precision must be 0 (fp32 CUDA cores), 1 (tf32 tcgen05 1x1 convs), 2 (1 + fused expand/depthwise blocks) or "
+                "3 (2 with 3xTF32 error-compensated tensor-core arithmetic: fp32-equivalent results)");
     if (desc->precision >= 1) { if (int rc = smk::tc_init()) return rc; }
     const bool tc = desc->precision >= 1;
     SmkEncoder* h = new SmkEncoder();
-    h->n_shape = desc->n_shape; h->n_exp = desc->n_exp; h->precision = tc ? 1 : 0; h->fuse_xdw = desc->precision == 2;
+    h->n_shape = desc->n_shape; h->n_exp = desc->n_exp; h->precision = tc ? 1 : 0; h->fuse_xdw = desc->precision >= 2; h->x3 = desc->precision == 3;
+    const bool x3 = h->x3;
     const int n_outs[3] = {6, desc->n_shape, desc->n_exp + 5};
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < 3; ++i) {
         const BlockDef* defs = i == 0 ? kSmall : kLarge;
         const int nb = i == 0 ? (int)(sizeof(kSmall) / sizeof(BlockDef)) : (int)(sizeof(kLarge) / sizeof(BlockDef));
         Backbone& bb = h->bb[i];
+        if (desc->n_tensors[i] == 0 || desc->tensors[i] == nullptr) continue;        // backbone not part of this handle
+        h->present[i] = true;
         TensorCursor cur{desc->tensors[i], desc->n_tensors[i]};
         bool ok = fold_conv(cur, 2, 3, 16, false, h->arena, &bb.stem, &e);
         int cin = 16, res = 112;
@@ -132,14 +150,14 @@ extern "C" int smk_encoder_create(const SmkEncoderDesc* desc, SmkEncoder** out) 
                 b.mid = cin;
                 ok = fold_conv(cur, 1, cin, cin, false, h->arena, &b.dw, &e);
                 if (ok && tc) { TensorCursor again = cur; ok = fold_conv(again, 0, cin, b.cout, false, h->arena, &b.pw_f32, &e); }
-                ok = ok && fold_conv(cur, 0, cin, b.cout, tc, h->arena, &b.pw, &e);
+                ok = ok && fold_conv(cur, 0, cin, b.cout, tc, h->arena, &b.pw, &e, x3);
             } else if (b.kind == IR) {
                 b.mid = make_divisible((double)cin * defs[k].exp);
-                ok = fold_conv(cur, 0, cin, b.mid, tc, h->arena, &b.pw, &e) && fold_conv(cur, 1, b.mid, b.mid, false, h->arena, &b.dw, &e) &&
-                     fold_conv(cur, 0, b.mid, b.cout, tc, h->arena, &b.pwl, &e);
+                ok = fold_conv(cur, 0, cin, b.mid, tc, h->arena, &b.pw, &e, x3) && fold_conv(cur, 1, b.mid, b.mid, false, h->arena, &b.dw, &e) &&
+                     fold_conv(cur, 0, b.mid, b.cout, tc, h->arena, &b.pwl, &e, x3);
             } else {
                 b.mid = cin;
-                ok = fold_conv(cur, 0, cin, b.cout, tc, h->arena, &b.pw, &e);
+                ok = fold_conv(cur, 0, cin, b.cout, tc, h->arena, &b.pw, &e, x3);
             }
             max_act = std::max(max_act, (size_t)res * res * b.mid);           // expanded tensor at input resolution
             res = (res + b.stride - 1) / b.stride;
@@ -165,11 +183,14 @@ extern "C" int smk_encoder_create(const SmkEncoderDesc* desc, SmkEncoder** out) 
         }
         if (e != cudaSuccess) { smk::set_error("smk_encoder_create: upload failed: %s", cudaGetErrorString(e)); delete h; return (int)e; }
     }
-    for (int s = 0; s < 2 && e == cudaSuccess; ++s) {
-        e = cudaStreamCreateWithFlags(&h->side[s], cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->join[s], cudaEventDisableTiming);
+    if (!h->present[0] && !h->present[1] && !h->present[2]) { smk::set_error("smk_encoder_create: no backbone given"); delete h; return -1; }
+    for (auto& f : h->forks) {
+        for (int s = 0; s < 2 && e == cudaSuccess; ++s) {
+            e = cudaStreamCreateWithFlags(&f.side[s], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f.join[s], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming);
     }
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming);
     if (e != cudaSuccess) { smk::set_error("smk_encoder_create: stream/event creation failed: %s", cudaGetErrorString(e)); delete h; return (int)e; }
     *out = h;
     return 0;
@@ -184,9 +205,9 @@ extern "C" size_t smk_encoder_workspace_bytes(const SmkEncoder* h, int B) {
 static int pointwise(const ConvW& c, const float* in, int B, int H, int W, bool relu, const float* res, float* out, cudaStream_t st) {
     if (c.wt) {
         smk::TcConv q{};
-        q.in = in; q.ld_in = c.cin; q.B = B; q.H = H; q.W = W; q.Cin = c.cin; q.wt = c.wt; q.scale = c.scale; q.bias = c.bias;
+        q.in = in; q.ld_in = c.cin; q.B = B; q.H = H; q.W = W; q.Cin = c.cin; q.wt = c.wt; q.wt_lo = c.wt_lo; q.scale = c.scale; q.bias = c.bias;
         q.N = c.cout; q.K = c.cin; q.mode = 0; q.relu = relu ? 1 : 0; q.res = res; q.ld_res = c.cout; q.res_pad = 0;
-        q.out = out; q.ld_out = c.cout; q.store = 0; q.round_out = 1;
+        q.out = out; q.ld_out = c.cout; q.store = 0; q.round_out = c.wt_lo ? 0 : 1;       // 3xTF32 consumers split full fp32 activations themselves
         return smk::tc_conv(q, st);
     }
     ConvProblem p{};
@@ -199,7 +220,9 @@ static int pointwise(const ConvW& c, const float* in, int B, int H, int W, bool 
 extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B, float* pose_cam, float* shape,
                                    float* expr, void* ws, size_t ws_bytes, void* stream) {
     if (B == 0) return 0;                      // empty batch: nothing to do (pointers may be null)
-    SMK_REQUIRE(h && img && pose_cam && shape && expr, "smk_encoder_forward: null argument");
+    SMK_REQUIRE(h && img, "smk_encoder_forward: null argument");
+    SMK_REQUIRE((pose_cam || !h->present[0]) && (shape || !h->present[1]) && (expr || !h->present[2]),
+                "smk_encoder_forward: null output for a backbone this handle holds");
     SMK_REQUIRE(B > 0, "smk_encoder_forward: negative batch");
     SMK_REQUIRE(ws && ws_bytes >= smk_encoder_workspace_bytes(h, B), "smk_encoder_forward: workspace too small");
     cudaStream_t main_st = (cudaStream_t)stream;
@@ -212,24 +235,30 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
     // fork the two large ones onto the handle's side streams so their many small, latency-bound layers
     // overlap; join before returning.  Event record/wait on other streams is legal under stream capture,
     // so a CUDA graph of the caller's stream gets three parallel branches.
-    const bool concurrent = !smk::profiling();   // the event profiler wants one kernel at a time
+    const int n_present = (int)h->present[0] + (int)h->present[1] + (int)h->present[2];
+    const bool concurrent = !smk::profiling() && n_present > 1;   // the event profiler wants one kernel at a time
+    const SmkEncoder::ForkSet& fk = h->forks[__atomic_fetch_add(&h->next_fork, 1u, __ATOMIC_RELAXED) % SmkEncoder::kForkSets];
     // precision 2: stem + block 0 (depthwise-separable, 16 channels at 112 x 112) run as one kernel per backbone —
     // the three largest activations never reach HBM.
     static const int fuse_stem_env = []() { const char* e = getenv("SMK_FUSE_STEM"); return e ? atoi(e) : 1; }();
-    const bool fuse_stem = h->fuse_xdw && fuse_stem_env && h->bb[0].blocks[0].kind == DS && h->bb[0].blocks[0].pw_f32.w;
-    if (!fuse_stem) {   // all three stems in one pass over the image (it is the only tensor the backbones share)
+    const bool fuse_stem = h->fuse_xdw && fuse_stem_env;                           // every backbone starts with a DS block
+    if (!fuse_stem && n_present == 3) {   // all three stems in one pass over the image (it is the only tensor the backbones share)
         const float* sw[3]; const float* ss[3]; const float* sb[3]; float* so[3];
         for (int i = 0; i < 3; ++i) { sw[i] = h->bb[i].stem.w; ss[i] = h->bb[i].stem.scale; sb[i] = h->bb[i].stem.bias; so[i] = bufs[i][0]; }
         if (int rc = smk::stem_conv3(img, B, 224, 224, sw, ss, sb, so, main_st)) return rc;
+    } else if (!fuse_stem) {
+        for (int i = 0; i < 3; ++i)
+            if (h->present[i]) { if (int rc = smk::stem_conv(img, B, 224, 224, h->bb[i].stem.w, h->bb[i].stem.scale, h->bb[i].stem.bias, bufs[i][0], main_st)) return rc; }
     }
     if (concurrent) {
-        SMK_CHECK_CUDA(cudaEventRecord(h->fork, main_st));
-        for (int s = 0; s < 2; ++s) SMK_CHECK_CUDA(cudaStreamWaitEvent(h->side[s], h->fork, 0));
+        SMK_CHECK_CUDA(cudaEventRecord(fk.fork, main_st));
+        for (int s = 0; s < 2; ++s) SMK_CHECK_CUDA(cudaStreamWaitEvent(fk.side[s], fk.fork, 0));
     }
     int rc = 0;                                   // first error; the side streams are joined on every path
     for (int i = 0; i < 3 && !rc; ++i) {
+        if (!h->present[i]) continue;
         const Backbone& bb = h->bb[i];
-        cudaStream_t st = (i == 0 || !concurrent) ? main_st : h->side[i - 1];
+        cudaStream_t st = (i == 0 || !concurrent) ? main_st : fk.side[i - 1];
         float* const* buf = bufs[i];
         float *x = buf[0], *y = buf[1], *e = buf[2], *d = buf[3];
         int res = 112;
@@ -237,14 +266,14 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
         if (fuse_stem) {
             const Block& b0 = bb.blocks[0];
             rc = smk::stem_ds(img, B, 224, 224, bb.stem.w, bb.stem.scale, bb.stem.bias, b0.dw.w, b0.dw.scale, b0.dw.bias,
-                              b0.pw_f32.w, b0.pw_f32.scale, b0.pw_f32.bias, b0.stride, 1, x, st);
+                              b0.pw_f32.w, b0.pw_f32.scale, b0.pw_f32.bias, b0.stride, h->x3 ? 0 : 1, x, st);
             res = 112 / b0.stride; first = 1;
         }
         for (size_t bi = first; bi < bb.blocks.size() && !rc; ++bi) {
             const Block& b = bb.blocks[bi];
             int ro = (res + b.stride - 1) / b.stride;
             if (b.kind == DS) {
-                rc = smk::dwconv3x3(x, B, res, res, b.cin, b.stride, b.dw.w, b.dw.scale, b.dw.bias, d, st, h->precision == 1);
+                rc = smk::dwconv3x3(x, B, res, res, b.cin, b.stride, b.dw.w, b.dw.scale, b.dw.bias, d, st, h->precision == 1 && !h->x3);
                 if (!rc) rc = pointwise(b.pw, d, B, ro, ro, false, b.skip ? x : nullptr, y, st);
             } else if (b.kind == IR) {
                 // The 7x7 layers (a 16x16 window holds 81 useful pixels, 49 outputs) run 3 % faster end to end as
@@ -253,12 +282,12 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
                 if (h->fuse_xdw && b.pw.wt && res >= xdw_min_res) {
                     // expand 1x1 + depthwise 3x3 in one kernel: the expanded tensor never leaves the SM
                     smk::XdwConv q{};
-                    q.x = x; q.B = B; q.H = res; q.W = res; q.Cin = b.cin; q.w1t = b.pw.wt; q.scale1 = b.pw.scale; q.bias1 = b.pw.bias;
-                    q.mid = b.mid; q.wdw = b.dw.w; q.scale2 = b.dw.scale; q.bias2 = b.dw.bias; q.stride = b.stride; q.round_out = 1; q.out = d;
+                    q.x = x; q.B = B; q.H = res; q.W = res; q.Cin = b.cin; q.w1t = b.pw.wt; q.w1t_lo = b.pw.wt_lo; q.scale1 = b.pw.scale; q.bias1 = b.pw.bias;
+                    q.mid = b.mid; q.wdw = b.dw.w; q.scale2 = b.dw.scale; q.bias2 = b.dw.bias; q.stride = b.stride; q.round_out = h->x3 ? 0 : 1; q.out = d;
                     rc = smk::xdw_conv(q, st);
                 } else {
                     rc = pointwise(b.pw, x, B, res, res, true, nullptr, e, st);
-                    if (!rc) rc = smk::dwconv3x3(e, B, res, res, b.mid, b.stride, b.dw.w, b.dw.scale, b.dw.bias, d, st, h->precision == 1);
+                    if (!rc) rc = smk::dwconv3x3(e, B, res, res, b.mid, b.stride, b.dw.w, b.dw.scale, b.dw.bias, d, st, h->precision == 1 && !h->x3);
                 }
                 if (!rc) rc = pointwise(b.pwl, d, B, ro, ro, false, b.skip ? x : nullptr, y, st);
             } else {
@@ -271,8 +300,8 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
         if (!rc) rc = smk::gap_linear(x, B, res * res, bb.feat, bb.head_w, bb.head_b, bb.n_out, bb.codes, y, outs[i], st);
     }
     for (int s = 0; s < 2 && concurrent; ++s) {   // join even after an error so a capturing stream is left consistent
-        cudaError_t e1 = cudaEventRecord(h->join[s], h->side[s]);
-        cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(main_st, h->join[s], 0) : e1;
+        cudaError_t e1 = cudaEventRecord(fk.join[s], fk.side[s]);
+        cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(main_st, fk.join[s], 0) : e1;
         if (!rc && e2 != cudaSuccess) { smk::set_error("smk_encoder_forward: stream join failed: %s", cudaGetErrorString(e2)); rc = (int)e2; }
     }
     return rc;

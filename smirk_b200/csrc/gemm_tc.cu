@@ -54,9 +54,10 @@ struct TcArgs {
     int round_out;                 // 1: round the stored activations to TF32 (round-to-nearest) for the next tensor-core layer
 };
 
-template <int BN, int STAGES, int MINB, bool PERSIST>
+template <int BN, int STAGES, int MINB, bool PERSIST, bool X3>
 __global__ void __launch_bounds__(NUM_THREADS, MINB)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+               const TcArgs a) {
     // Output tiles (128 rows x BN columns) are strided over the grid.
     //   PERSIST = true : grid = resident CTAs; the smem ring runs across tile boundaries and the accumulator is
     //                    double-buffered in TMEM, so the TMA loads and MMAs of tile i+1 overlap the epilogue of
@@ -64,8 +65,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     //   PERSIST = false: grid = tiles, one tile per CTA, the epilogue staging slab aliases the (by then idle)
     //                    first ring stage and TMEM holds one accumulator: smaller footprint -> 3-5 CTAs per SM,
     //                    which is what the shallow-K streaming 1x1 layers want (more epilogue warps in flight).
+    //   X3 = true      : error-compensated "3xTF32" arithmetic (fp32-equivalent results on the tensor cores).  Every fp32
+    //                    operand is split into a TF32 head and a TF32 tail, a = a_hi + a_lo, and three products are
+    //                    accumulated: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (the dropped a_lo*w_lo term is ~2^-22 relative).
+    //                    Weights are split on the host (tmBlo maps the tails); the activation tile is split in shared
+    //                    memory by the epilogue warps, which are otherwise idle during the main loop of a single-tile
+    //                    CTA: they rewrite the landed A tile with its heads (so the tensor core sees exact TF32 words
+    //                    whatever it does with the low mantissa bits) and write the tails to a second tile.
+    static_assert(!X3 || !PERSIST, "the 3xTF32 split borrows the epilogue warps: single-tile CTAs only");
     constexpr int B_STAGE_BYTES = BN * BKB;
-    constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    constexpr int HALF_STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    constexpr int STAGE_BYTES = (X3 ? 2 : 1) * HALF_STAGE_BYTES;
     constexpr uint32_t TMEM_COLS = PERSIST ? 2 * BN : BN;   // 32..256: powers of two
     constexpr uint32_t IDESC = make_idesc(BM, BN);
     extern __shared__ uint8_t smem_raw[];
@@ -77,14 +87,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* empty = full + STAGES;
     uint64_t* acc_full = empty + STAGES;
     uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* split = acc_empty + 2;                                    // X3: "stage s has been split" (4 epilogue warps arrive)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(split + STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&split[s], 4); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -112,7 +124,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&empty[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
                     uint8_t* sa = smem + s * STAGE_BYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
-                    mbar_expect_tx(&full[s], (uint32_t)STAGE_BYTES);
+                    mbar_expect_tx(&full[s], (uint32_t)(HALF_STAGE_BYTES + (X3 ? B_STAGE_BYTES : 0)));
+                    if (X3) tma_load_2d(&tmBlo, sa + HALF_STAGE_BYTES + A_STAGE_BYTES, &full[s], kb * BK, n0);
                     if (a.mode == 0) {
                         tma_load_2d(&tmA, sa, &full[s], kb * BK, m0);
                     } else {
@@ -134,7 +147,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tcgen05_fence_after();
                 for (int kb = 0; kb < a.nkb; ++kb, ++it) {
                     const int s = it % STAGES;
-                    mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
+                    mbar_wait(X3 ? &split[s] : &full[s], (uint32_t)(it / STAGES) & 1u);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                     const uint32_t sb = sa + A_STAGE_BYTES;
@@ -143,6 +156,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         uint64_t da = make_smem_desc(sa + k * UMMA_K * 4);
                         uint64_t db = make_smem_desc(sb + k * UMMA_K * 4);
                         umma_tf32(tmem_base + (uint32_t)(buf * BN), da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+                        if (X3) {
+                            uint64_t dal = make_smem_desc(sa + HALF_STAGE_BYTES + k * UMMA_K * 4);
+                            uint64_t dbl = make_smem_desc(sb + HALF_STAGE_BYTES + k * UMMA_K * 4);
+                            umma_tf32(tmem_base + (uint32_t)(buf * BN), dal, db, IDESC, 1u);      // a_lo * w_hi
+                            umma_tf32(tmem_base + (uint32_t)(buf * BN), da, dbl, IDESC, 1u);      // a_hi * w_lo
+                        }
                     }
                     tcgen05_commit(&empty[s]);          // frees this smem stage once the MMAs above have read it
                 }
@@ -159,6 +178,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         //      scale/bias (+residual) (+ReLU) (+TF32 rounding) and store — every global access of the
         //      warp now covers whole 128-byte lines of 4 output rows instead of 16 bytes of 32 rows.
         const int quarter = warp & 3;
+        if (X3) {
+            // ===== 3xTF32: split every landed A tile into TF32 heads (in place) and tails (second tile) =====
+            const int t = threadIdx.x - 64;                        // 0..127
+            for (int kb = 0; kb < a.nkb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&full[s], (uint32_t)(kb / STAGES) & 1u);
+                float4* A = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+                float4* AL = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + HALF_STAGE_BYTES);
+#pragma unroll
+                for (int j = 0; j < A_STAGE_BYTES / 16 / 128; ++j) {
+                    const float4 v = A[t + 128 * j];
+                    float4 hi, lo;
+                    hi.x = smk::round_tf32(v.x); hi.y = smk::round_tf32(v.y); hi.z = smk::round_tf32(v.z); hi.w = smk::round_tf32(v.w);
+                    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;       // exact
+                    A[t + 128 * j] = hi; AL[t + 128 * j] = lo;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&split[s]);
+            }
+        }
         uint8_t* slab = slabs + quarter * 4096;
         const int sub = lane >> 3, jj = lane & 7;              // phase-2 role: row-in-group, 16-byte chunk
         int tc = 0;
@@ -311,9 +351,9 @@ int encode_im2col(CUtensorMap* map, const float* base, int B, int Hin, int Win, 
     return 0;
 }
 
-template <int BN, int STAGES, int MINB, bool PERSIST>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a_in, cudaStream_t st) {
-    constexpr size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * BKB) + (PERSIST ? SLAB_BYTES : 0) + 1024 + 256;
+template <int BN, int STAGES, int MINB, bool PERSIST, bool X3 = false>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a_in, cudaStream_t st, const CUtensorMap* tmBlo = nullptr) {
+    constexpr size_t smem = (size_t)STAGES * (X3 ? 2 : 1) * (A_STAGE_BYTES + BN * BKB) + (PERSIST ? SLAB_BYTES : 0) + 1024 + 256;
     static_assert(MINB * (smem + 1024) <= 228 * 1024, "shared memory budget of MINB resident CTAs");
     static_assert(MINB * (PERSIST ? 2 : 1) * BN <= 512, "TMEM budget of MINB resident CTAs");
     // The attribute is per device and per function; set it once per (device, instantiation).  One bit per
@@ -322,14 +362,14 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a_in, c
     int dev = 0;
     SMK_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !(configured_mask & (1ull << dev))) {
-        SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, MINB, PERSIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, MINB, PERSIST, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev < 64) configured_mask |= 1ull << dev;
     }
     TcArgs a = a_in;
     a.tiles_n = cdiv(a.N, BN);
     a.n_tiles = cdiv(a.M, BM) * a.tiles_n;
     dim3 grid((unsigned)(PERSIST ? std::min(a.n_tiles, MINB * 148) : a.n_tiles));
-    SMK_LAUNCH((gemm_tc_kernel<BN, STAGES, MINB, PERSIST>), dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB, a);
+    SMK_LAUNCH((gemm_tc_kernel<BN, STAGES, MINB, PERSIST, X3>), dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB, tmBlo ? *tmBlo : tmB, a);
     SMK_CHECK_LAUNCH();
     return 0;
 }
@@ -376,11 +416,19 @@ int tc_conv(const TcConv& p, cudaStream_t st) {
     if (int rc = encode_2d(&tmB, p.wt, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, (uint32_t)BN)) return rc;
     {
         const double cin_eff = p.mode == 0 ? p.K : p.Cin;
-        const char* tag = p.mode == 0 ? (p.store == 1 ? "upconv_gemm_tc" : "pw_gemm_tc") : "conv3x3_gemm_tc";
+        const char* tag = p.mode == 0 ? (p.store == 1 ? "upconv_gemm_tc" : (p.wt_lo ? "pw_gemm_tc3x" : "pw_gemm_tc")) : "conv3x3_gemm_tc";
         if (g_prof_detail) tag = prof_shape_tag(tag, M, p.K, p.N);
         SMK_TAG(tag,
                 4.0 * ((double)M * cin_eff + (double)p.K * p.N + (double)M * p.N * (p.res ? 2 : 1) + 2.0 * p.N),
                 2.0 * (double)M * p.N * p.K, st);
+    }
+    if (p.wt_lo) {                                      // 3xTF32: fp32-equivalent arithmetic (encoder precision 3)
+        SMK_REQUIRE(p.mode == 0 && p.store == 0, "tc_conv: the 3xTF32 path covers plain 1x1 convolutions / GEMMs");
+        CUtensorMap tmBlo;
+        if (int rc = encode_2d(&tmBlo, p.wt_lo, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, (uint32_t)BN)) return rc;
+        if (BN == 32) return launch<32, 2, 2, false, true>(tmA, tmB, a, st, &tmBlo);
+        if (BN == 64) return launch<64, 2, 2, false, true>(tmA, tmB, a, st, &tmBlo);
+        return launch<128, 2, 1, false, true>(tmA, tmB, a, st, &tmBlo);
     }
     if (deep_small && BN == 32) return launch<32, 8, 1, false>(tmA, tmB, a, st);
     if (deep_small && BN == 64) return launch<64, 8, 1, false>(tmA, tmB, a, st);
@@ -422,6 +470,14 @@ extern "C" int smk_debug_conv_tc(const float* in, int ld_in, int B, int H, int W
     smk::TcConv p{};
     p.in = in; p.ld_in = ld_in; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.wt = wt; p.scale = scale; p.bias = bias; p.N = N; p.K = K;
     p.mode = mode; p.relu = relu; p.res = res; p.ld_res = ld_res; p.res_pad = res_pad; p.out = out; p.ld_out = ld_out; p.store = store;
+    return smk::tc_conv(p, (cudaStream_t)stream);
+}
+// 1x1 conv / GEMM on the 3xTF32 path: wt_hi / wt_lo are the TF32 heads and tails of the [N][K] weights.
+extern "C" int smk_debug_gemm_tc3x(const float* in, int ld_in, int M, const float* wt_hi, const float* wt_lo, const float* scale,
+                                   const float* bias, int N, int K, int relu, const float* res, int ld_res, float* out, int ld_out, void* stream) {
+    smk::TcConv p{};
+    p.in = in; p.ld_in = ld_in; p.B = 1; p.H = 1; p.W = M; p.Cin = K; p.wt = wt_hi; p.wt_lo = wt_lo; p.scale = scale; p.bias = bias; p.N = N; p.K = K;
+    p.mode = 0; p.relu = relu; p.res = res; p.ld_res = ld_res; p.res_pad = 0; p.out = out; p.ld_out = ld_out; p.store = 0; p.round_out = 0;
     return smk::tc_conv(p, (cudaStream_t)stream);
 }
 extern "C" int smk_debug_reflect_halo(float* buf, int B, int H, int W, int C, void* stream) {

@@ -8,6 +8,7 @@ struct TcConv {
     const float* in; int ld_in;          // NHWC input, pixel stride ld_in (mode 2: buffer is [B,H+2,W+2,*], reflection padded)
     int B, H, W, Cin;                    // OUTPUT spatial dims H x W (stride-1 convs), input channels
     const float* wt;                     // [N][K], k fastest, k = (ky*3+kx)*Cin + c for 3x3
+    const float* wt_lo;                  // non-null: TF32 tails of the weights (wt holds the heads) -> 3xTF32 arithmetic
     const float* scale; const float* bias;
     int N, K;
     int mode;                            // 0: 1x1 / plain GEMM, 1: 3x3 zero pad 1, 2: 3x3 over a pre-padded buffer

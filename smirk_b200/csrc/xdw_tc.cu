@@ -33,7 +33,7 @@ constexpr int WIN = 16;                         // window edge (pixels of e)
 constexpr int HALF_BYTES = 128 * BKB;           // one 16x8-pixel box, 32 channels: 16 KiB
 constexpr int NC = 32;                          // expanded channels per chunk
 constexpr int B_BYTES = NC * BKB;               // 4 KiB
-constexpr int STAGE_BYTES = 2 * HALF_BYTES + B_BYTES;   // 36 KiB
+constexpr int STAGE_BYTES = 2 * HALF_BYTES + B_BYTES;   // 36 KiB (x2 in the 3xTF32 variant: heads + tails)
 #ifndef SMK_XDW_STAGES
 #define SMK_XDW_STAGES 2
 #endif
@@ -44,6 +44,7 @@ constexpr int PAR_ROWS = 13;                     // scale1, bias1, 9 depthwise t
 constexpr int PAR_BYTES = 2 * PAR_ROWS * NC * 4;  // double-buffered: 3328 B
 constexpr int NUM_WORKERS = 256;
 constexpr int NUM_THREADS = 64 + NUM_WORKERS;
+constexpr int NUM_SPLITTERS = 128;              // 3xTF32 variant: four more warps split the landed x window into TF32 heads / tails
 constexpr uint32_t TMEM_COLS = 128;             // (2 buffers) x (2 halves) x 32 columns
 
 using namespace ptx;                            // PTX wrappers shared by the tcgen05 kernels (tc_ptx.cuh)
@@ -64,10 +65,16 @@ struct XdwArgs {
     int round_out;
 };
 
-template <int STRIDE>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
-xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const XdwArgs a) {
+// X3 = true: error-compensated 3xTF32 expand GEMM (fp32-equivalent e): x = x_hi + x_lo split in shared memory by four
+// dedicated warps (heads rewritten in place, tails in a second window), w1 = w_hi + w_lo split on the host (tmWlo);
+// e = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo accumulated in the same TMEM columns.  One CTA per SM (184 KB of shared memory).
+template <int STRIDE, bool X3>
+__global__ void __launch_bounds__(NUM_THREADS + (X3 ? NUM_SPLITTERS : 0), X3 ? 1 : 2)
+xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
+           const XdwArgs a) {
     constexpr int TO = STRIDE == 1 ? 14 : 7;                    // output tile edge
+    constexpr int STAGE_BYTES = (X3 ? 2 : 1) * smk::STAGE_BYTES;  // [x half 0][x half 1][w] (+ the same three again: tails)
+    constexpr int LO = smk::STAGE_BYTES;                        // offset of the tails within a stage
     constexpr uint32_t IDESC = make_idesc(128, NC);
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B; offset arithmetic (not an integer round-trip of the pointer) keeps
@@ -79,7 +86,8 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     uint64_t* empty = full + STAGES;
     uint64_t* acc_full = empty + STAGES;
     uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* split = acc_empty + 2;                            // X3: stage s has been split (4 splitter warps arrive)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(split + STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // Persistent CTA: work item = (image, output tile, channel-chunk group), items strided over the grid.
@@ -100,7 +108,8 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWlo) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&split[s], NUM_SPLITTERS / 32); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NUM_WORKERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -126,10 +135,11 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                         const int s = it % STAGES;
                         mbar_wait(&empty[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
                         uint8_t* st = smem + s * STAGE_BYTES;
-                        mbar_expect_tx(&full[s], (uint32_t)STAGE_BYTES);
+                        mbar_expect_tx(&full[s], (uint32_t)(smk::STAGE_BYTES + (X3 ? B_BYTES : 0)));
                         tma_load_4d(&tmX, st, &full[s], kb * BK, ex0, ey0, w.img);
                         tma_load_4d(&tmX, st + HALF_BYTES, &full[s], kb * BK, ex0, ey0 + 8, w.img);
                         tma_load_2d(&tmW, st + 2 * HALF_BYTES, &full[s], kb * BK, c * NC);
+                        if (X3) tma_load_2d(&tmWlo, st + LO + 2 * HALF_BYTES, &full[s], kb * BK, c * NC);
                     }
             }
         }
@@ -145,21 +155,53 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                 tcgen05_fence_after();
                 for (int kb = 0; kb < a.nkb; ++kb, ++it) {
                     const int s = it % STAGES;
-                    mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
+                    mbar_wait(X3 ? &split[s] : &full[s], (uint32_t)(it / STAGES) & 1u);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                     const uint32_t sb = sa + 2 * HALF_BYTES;
 #pragma unroll
                     for (int half = 0; half < 2; ++half)
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k)
-                            umma_tf32(tmem_base + (uint32_t)((buf * 2 + half) * NC), make_smem_desc(sa + half * HALF_BYTES + k * UMMA_K * 4),
-                                      make_smem_desc(sb + k * UMMA_K * 4), IDESC, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint32_t d = tmem_base + (uint32_t)((buf * 2 + half) * NC);
+                            const uint64_t da = make_smem_desc(sa + half * HALF_BYTES + k * UMMA_K * 4);
+                            const uint64_t db = make_smem_desc(sb + k * UMMA_K * 4);
+                            umma_tf32(d, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+                            if (X3) {
+                                umma_tf32(d, make_smem_desc(sa + LO + half * HALF_BYTES + k * UMMA_K * 4), db, IDESC, 1u);   // x_lo * w_hi
+                                umma_tf32(d, da, make_smem_desc(sb + LO + k * UMMA_K * 4), IDESC, 1u);                       // x_hi * w_lo
+                            }
+                        }
                     tcgen05_commit(&empty[s]);
                 }
                 tcgen05_commit(&acc_full[buf]);
               }
             }
+        }
+    } else if (X3 && warp >= 2 + NUM_WORKERS / 32) {
+        // ===== splitters (3xTF32): x window -> TF32 heads in place + tails, one ring stage at a time =====
+        const int t = threadIdx.x - (64 + NUM_WORKERS);    // 0..127
+        int it = 0;
+        for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+            const Item w = decode(item);
+            for (int c = w.c_begin; c < w.c_end; ++c)
+                for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
+                    float4* X = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+                    float4* XL = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + LO);
+#pragma unroll 4
+                    for (int j = 0; j < 2 * HALF_BYTES / 16 / NUM_SPLITTERS; ++j) {
+                        const float4 v = X[t + NUM_SPLITTERS * j];
+                        float4 hi, lo;
+                        hi.x = round_tf32(v.x); hi.y = round_tf32(v.y); hi.z = round_tf32(v.z); hi.w = round_tf32(v.w);
+                        lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;       // exact
+                        X[t + NUM_SPLITTERS * j] = hi; XL[t + NUM_SPLITTERS * j] = lo;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&split[s]);
+                }
         }
     } else {
         // ===== workers: 8 warps =====
@@ -336,7 +378,7 @@ int xdw_conv(const XdwConv& p, cudaStream_t st) {
     SMK_REQUIRE(p.stride == 1 || (p.H % 2 == 0 && p.W % 2 == 0), "xdw_conv: stride 2 expects even input sizes (TF-SAME pad_begin 0)");
     const int Ho = (p.H + p.stride - 1) / p.stride, Wo = (p.W + p.stride - 1) / p.stride;
     const int TO = p.stride == 1 ? 14 : 7;
-    CUtensorMap tmX, tmW;
+    CUtensorMap tmX, tmW, tmWlo;
     {
         cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
         cuuint64_t strides[3] = {(cuuint64_t)p.Cin * 4, (cuuint64_t)p.W * p.Cin * 4, (cuuint64_t)p.H * p.W * p.Cin * 4};
@@ -354,6 +396,12 @@ int xdw_conv(const XdwConv& p, cudaStream_t st) {
         CUresult r = g_encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p.w1t, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SMK_REQUIRE(r == CUDA_SUCCESS, "xdw_conv: cuTensorMapEncodeTiled(w1) failed (%d): mid=%d Cin=%d", (int)r, p.mid, p.Cin);
+        tmWlo = tmW;
+        if (p.w1t_lo) {
+            r = g_encode(&tmWlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p.w1t_lo, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            SMK_REQUIRE(r == CUDA_SUCCESS, "xdw_conv: cuTensorMapEncodeTiled(w1 tails) failed (%d)", (int)r);
+        }
     }
     static const int slots_lo = []() { const char* e = getenv("SMK_XDW_SLOTS"); return e ? atoi(e) : 148; }();   // resident CTAs to aim for: one per SM leaves half of every SM to concurrent kernels (+4 % end to end vs 296)
     static const int slots_hi = []() { const char* e = getenv("SMK_XDW_SLOTS_HI"); return e ? atoi(e) : 0; }();  // layers with >= 296 output tiles (0: same as SMK_XDW_SLOTS)
@@ -370,25 +418,34 @@ int xdw_conv(const XdwConv& p, cudaStream_t st) {
     a.tiles_x = cdiv(Wo, TO); a.tiles_y = cdiv(Ho, TO);
     a.scale1 = p.scale1; a.bias1 = p.bias1; a.wdw = p.wdw; a.scale2 = p.scale2; a.bias2 = p.bias2; a.out = p.out; a.round_out = p.round_out;
     constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + E_BYTES + PAR_BYTES + 1024 + 256;
+    constexpr size_t smem3 = (size_t)STAGES * 2 * STAGE_BYTES + E_BYTES + PAR_BYTES + 1024 + 256;
     static_assert(2 * (smem + 1024) <= 228 * 1024, "two CTAs per SM");
+    static_assert(smem3 + 1024 <= 227 * 1024, "3xTF32 variant: one CTA per SM");
     static unsigned long long configured_mask = 0;       // per-device attribute, see gemm_tc.cu
     int dev = 0;
     SMK_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !(configured_mask & (1ull << dev))) {
-        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
         if (dev < 64) configured_mask |= 1ull << dev;
     }
     {
         const double px_in = (double)p.B * p.H * p.W, px_out = (double)p.B * Ho * Wo;
-        const char* tag = "xdw_fused_tc";
+        const char* tag = p.w1t_lo ? "xdw_fused_tc3x" : "xdw_fused_tc";
         if (g_prof_detail) tag = prof_shape_tag(tag, (long)px_out, p.Cin, p.mid);
         SMK_TAG(tag, 4.0 * (px_in * p.Cin + px_out * p.mid + (double)p.mid * (p.Cin + 13)), 2.0 * px_in * p.Cin * p.mid + 18.0 * px_out * p.mid, st);
     }
     a.n_items = a.tiles_x * a.tiles_y * p.B * a.groups;
-    dim3 grid((unsigned)std::min(a.n_items, slots));            // persistent: (up to) 2 CTAs per SM
-    if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1>), dim3(grid), dim3(NUM_THREADS), smem, st, tmX, tmW, a);
-    else SMK_LAUNCH((xdw_kernel<2>), dim3(grid), dim3(NUM_THREADS), smem, st, tmX, tmW, a);
+    dim3 grid((unsigned)std::min(a.n_items, p.w1t_lo ? std::min(slots, 148) : slots));            // persistent: (up to) 2 CTAs per SM
+    if (p.w1t_lo) {
+        if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, true>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3, st, tmX, tmW, tmWlo, a);
+        else SMK_LAUNCH((xdw_kernel<2, true>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3, st, tmX, tmW, tmWlo, a);
+    } else {
+        if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, false>), dim3(grid), dim3(NUM_THREADS), smem, st, tmX, tmW, tmWlo, a);
+        else SMK_LAUNCH((xdw_kernel<2, false>), dim3(grid), dim3(NUM_THREADS), smem, st, tmX, tmW, tmWlo, a);
+    }
     SMK_CHECK_LAUNCH();
     return 0;
 }
@@ -401,5 +458,14 @@ extern "C" int smk_debug_xdw(const float* x, int B, int H, int W, int Cin, const
     smk::XdwConv p{};
     p.x = x; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.w1t = w1t; p.scale1 = scale1; p.bias1 = bias1; p.mid = mid; p.wdw = wdw;
     p.scale2 = scale2; p.bias2 = bias2; p.stride = stride; p.round_out = round_out; p.out = out;
+    return smk::xdw_conv(p, (cudaStream_t)stream);
+}
+
+extern "C" int smk_debug_xdw3x(const float* x, int B, int H, int W, int Cin, const float* w1t_hi, const float* w1t_lo, const float* scale1,
+                               const float* bias1, int mid, const float* wdw, const float* scale2, const float* bias2, int stride,
+                               float* out, void* stream) {
+    smk::XdwConv p{};
+    p.x = x; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.w1t = w1t_hi; p.w1t_lo = w1t_lo; p.scale1 = scale1; p.bias1 = bias1; p.mid = mid; p.wdw = wdw;
+    p.scale2 = scale2; p.bias2 = bias2; p.stride = stride; p.round_out = 0; p.out = out;
     return smk::xdw_conv(p, (cudaStream_t)stream);
 }

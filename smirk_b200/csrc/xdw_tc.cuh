@@ -8,6 +8,7 @@ struct XdwConv {
     const float* x;                       // [B,H,W,Cin] NHWC, contiguous
     int B, H, W, Cin;
     const float* w1t;                     // 1x1 expand weights [mid][Cin] (K-major, TF32-rounded)
+    const float* w1t_lo;                  // non-null: TF32 tails of the weights (w1t holds the heads) -> 3xTF32 arithmetic
     const float* scale1; const float* bias1;     // folded BN after the 1x1 conv (ReLU follows)
     int mid;
     const float* wdw;                     // depthwise weights [9][mid]

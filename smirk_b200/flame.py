@@ -102,9 +102,10 @@ class FLAME(nn.Module):
             raise RuntimeError("smirk_b200.FLAME: unsupported kinematic tree %s" % self.parents.tolist())
         self._handle, self._handle_dev, self._ws = None, None, _lib.Workspace()
 
-    # -- native handle ------------------------------------------------------------------------------
+    # -- native handle (re-packed when a buffer is replaced / edited in place / moved) ---------------
     def _native(self, device):
-        if self._handle is not None and self._handle_dev == device:
+        sig = _lib.buffers_signature(self, device)
+        if self._handle is not None and self._handle_dev == sig:
             return self._handle
         self._release()
         L = _lib.lib()
@@ -130,19 +131,11 @@ class FLAME(nn.Module):
         h = C.c_void_p()
         with torch.cuda.device(device):
             _lib.check(L.smk_flame_create(C.byref(d), C.byref(h)), "smk_flame_create")
-        self._handle, self._handle_dev = h, device
-        return h
+        self._handle, self._handle_dev = _lib.NativeHandle(h, "smk_flame_destroy"), sig
+        return self._handle
 
     def _release(self):
-        if getattr(self, "_handle", None) is not None:
-            try:
-                _lib.lib().smk_flame_destroy(self._handle)
-            except Exception:
-                pass
-            self._handle = None
-
-    def __del__(self):
-        self._release()
+        self._handle = None                    # the native object dies with its last reference (_lib.NativeHandle)
 
     def __deepcopy__(self, memo):
         import copy

@@ -14,7 +14,13 @@ This is the public entry point ``bench.py`` and the demos use for batched work:
                               results into pinned buffers; lane i % slots, copies on a second stream, so
                               the copies of one batch overlap the kernels of the other;
 * ``shard_bounds`` / ``all_gather_frames``  frame-shard data parallelism (one process per GPU, contiguous
-                              split of the batch; a single NCCL all-gather of the final outputs — SURVEY.md §8e).
+                              split of the batch; a single NCCL all-gather of the final outputs — SURVEY.md §8e);
+* ``enable_gather(keys)``     puts that all-gather INTO the pipeline: after every batch the lane's outputs are gathered
+                              over all ranks on a communication stream (NCCL over NVLink / NVSwitch), overlapping the
+                              kernels of the next batches on the other lanes.
+
+Captured graphs snapshot the packed weights and workspaces they were recorded with and keep them alive
+(``rec["keep"]``); after changing weights, ``precision`` or devices call ``refresh()`` to re-capture.
 """
 import copy
 
@@ -63,6 +69,11 @@ class _Lane:
         self.done = torch.cuda.Event()
         self.staged = torch.cuda.Event()
         self.consumed = torch.cuda.Event()
+        self.gathered = torch.cuda.Event()
+        self.gather_out = {}
+
+    def modules(self):
+        return [m for m in (self.encoder, self.flame, self.renderer, self.generator) if m is not None]
 
 
 class SmirkPipeline:
@@ -74,6 +85,13 @@ class SmirkPipeline:
         self.slots = max(1, int(slots))
         self._lanes = [_Lane((encoder, flame, renderer, generator), self.device, own_stream=False)]
         self._h2d = self._d2h = None
+        self._gather_keys, self._gather_group, self._comm = (), None, None
+
+    def refresh(self):
+        """Drop every captured graph (and the weights / workspaces they kept alive) and the lane replicas, so the next
+        call re-captures from the current state of the caller's modules."""
+        torch.cuda.synchronize(self.device)
+        self._lanes = [_Lane((self.encoder, self.flame, self.renderer, self.generator), self.device, own_stream=False)]
 
     def _lane(self, i):
         """Lane 0 runs the caller's modules on the caller's stream; lanes >= 1 are replicas (deep copies:
@@ -126,7 +144,12 @@ class SmirkPipeline:
         with torch.cuda.graph(g):
             static_out = self.forward(static_in, static_mask, lane)
         launches = _lib.lib().smk_launch_count() - n0
-        rec = dict(graph=g, img=static_in, mask=static_mask, out=static_out, launches=int(launches))
+        # The graph holds raw pointers into each module's packed weights (native handle) and workspace: keep both
+        # alive for as long as the graph exists, whatever the modules do afterwards (re-pack, grow their workspace
+        # for a larger batch, ...).  A workspace that grows allocates a NEW buffer, so graphs of different batch
+        # sizes on one lane never alias a freed one.
+        keep = [(m._handle, m._ws.buf) for m in L.modules()]
+        rec = dict(graph=g, img=static_in, mask=static_mask, out=static_out, launches=int(launches), keep=keep)
         L.graphs[B] = rec
         return rec
 
@@ -149,22 +172,73 @@ class SmirkPipeline:
         L = self._lanes[lane]
         cur = torch.cuda.current_stream(self.device)
         if L.stream is None:
+            if self._gather_keys:
+                cur.wait_event(L.gathered)
             self.replay(img, masked_img)
+            L.computed.record(cur)
+            self._gather(L, rec)
             return rec["out"]
         L.stream.wait_stream(cur)                           # inputs ready
         with torch.cuda.stream(L.stream):
+            if self._gather_keys:
+                L.stream.wait_event(L.gathered)             # the previous all-gather of this lane has read the outputs
             rec["img"].copy_(img, non_blocking=True)
             if rec["mask"] is not None:
                 rec["mask"].copy_(masked_img, non_blocking=True)
             rec["graph"].replay()
+            L.computed.record(L.stream)
+        self._gather(L, rec)
         return rec["out"]
+
+    # ---- all-gather of the final outputs inside the pipeline (frame-shard data parallelism) ----------------
+    def enable_gather(self, keys=("rendered_img", "vertices", "params"), group=None):
+        """After every batch, all-gather the listed outputs over the process group (dim 0 = rank-major frames) on a
+        communication stream; results land in ``gathered(i)``.  ``keys = ()`` switches it off.  NCCL rides NVLink 5 /
+        NVSwitch; the collective of batch i overlaps the kernels of batches i+1.. on the other lanes."""
+        import torch.distributed as dist
+        self._gather_keys = tuple(keys) if (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1) else ()
+        self._gather_group = group
+        if self._gather_keys and self._comm is None:
+            self._comm = torch.cuda.Stream(device=self.device)
+        return self._gather_keys
+
+    def _gather(self, L, rec):
+        if not self._gather_keys:
+            return
+        import torch.distributed as dist
+        ws = dist.get_world_size(self._gather_group)
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(L.computed)
+            for k in self._gather_keys:
+                t = rec["out"][k]
+                key = (k, tuple(t.shape))
+                if key not in L.gather_out:
+                    L.gather_out[key] = torch.empty((ws * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+                dist.all_gather_into_tensor(L.gather_out[key], t, group=self._gather_group)
+            L.gathered.record(self._comm)
+
+    def gathered(self, i, key):
+        """The all-gathered ``key`` of the batch last submitted on lane ``i % slots`` (valid after ``join()``)."""
+        L = self._lanes[i % self.slots]
+        for (k, _), v in L.gather_out.items():
+            if k == key:
+                return v
+        raise KeyError(key)
+
+    def gather_bytes_per_step(self, B):
+        """Bytes this rank RECEIVES per step in the all-gather (world_size x its own shard)."""
+        if not self._gather_keys:
+            return 0
+        import torch.distributed as dist
+        rec = self.capture(B)
+        return dist.get_world_size(self._gather_group) * sum(rec["out"][k].numel() * rec["out"][k].element_size() for k in self._gather_keys)
 
     def join(self):
         cur = torch.cuda.current_stream(self.device)
         for L in self._lanes:
             if L.stream is not None:
                 cur.wait_stream(L.stream)
-        for st in (getattr(self, "_h2d", None), getattr(self, "_d2h", None)):
+        for st in (getattr(self, "_h2d", None), getattr(self, "_d2h", None), getattr(self, "_comm", None)):
             if st is not None:
                 cur.wait_stream(st)
 
@@ -210,6 +284,8 @@ class SmirkPipeline:
         with torch.cuda.stream(compute):
             compute.wait_event(L.staged)
             compute.wait_event(L.done)                      # output staging drained by the previous D2H of this lane
+            if self._gather_keys:
+                compute.wait_event(L.gathered)
             rec["img"].copy_(hb["dev_in"], non_blocking=True)
             if rec["mask"] is not None:
                 rec["mask"].copy_(hb["dev_mask"], non_blocking=True)
@@ -218,6 +294,7 @@ class SmirkPipeline:
             for k in keys:
                 hb["dev_out"][k].copy_(rec["out"][k], non_blocking=True)
             L.computed.record(compute)
+        self._gather(L, rec)
         with torch.cuda.stream(self._d2h):
             self._d2h.wait_event(L.computed)
             for k in keys:

@@ -83,7 +83,8 @@ class Renderer(nn.Module):
         self._handle, self._handle_dev, self._ws = None, None, _lib.Workspace()
 
     def _native(self, device):
-        if self._handle is not None and self._handle_dev == device:
+        sig = (str(device), self.faces._version, self.faces.data_ptr(), self.image_size)
+        if self._handle is not None and self._handle_dev == sig:
             return self._handle
         self._release()
         L = _lib.lib()
@@ -95,19 +96,11 @@ class Renderer(nn.Module):
         h = C.c_void_p()
         with torch.cuda.device(device):
             _lib.check(L.smk_renderer_create(C.byref(d), C.byref(h)), "smk_renderer_create")
-        self._handle, self._handle_dev = h, device
-        return h
+        self._handle, self._handle_dev = _lib.NativeHandle(h, "smk_renderer_destroy"), sig
+        return self._handle
 
     def _release(self):
-        if getattr(self, "_handle", None) is not None:
-            try:
-                _lib.lib().smk_renderer_destroy(self._handle)
-            except Exception:
-                pass
-            self._handle = None
-
-    def __del__(self):
-        self._release()
+        self._handle = None                    # the native object dies with its last reference (_lib.NativeHandle)
 
     def __deepcopy__(self, memo):
         import copy
@@ -153,6 +146,10 @@ class Renderer(nn.Module):
                 _lib.check(L.smk_project_points(_lib.ptr(pts), _lib.ptr(cam), B, pts.shape[1], _lib.ptr(xy), st),
                            "smk_project_points")
                 out[k] = xy
+        if self.render_full_head:
+            # renderer.py:140-144: with the full head the fancy-index is skipped, so the in-place `z += 10` of render()
+            # also lands in the tensor the reference returns as `transformed_vertices`
+            tverts[..., 2] += 10.0
         if raw:
             out.update(pix_to_face=p2f, bary=bary, zbuf=zbuf, normals=normals)
         return out

@@ -107,76 +107,35 @@ def create_backbone(backbone_name, pretrained=True):
     return bb, bb.feature_dim
 
 
-class PoseEncoder(nn.Module):
-    def __init__(self):
-        super().__init__()
-        self.encoder, feature_dim = create_backbone("tf_mobilenetv3_small_minimal_100")
-        self.pose_cam_layers = nn.Sequential(nn.Linear(feature_dim, 6))
-        self.init_weights()
+class _NativeEncoder(nn.Module):
+    """Shared machinery of SmirkEncoder and its three sub-encoders: a native handle over the backbones returned by
+    ``_parts()`` (slot 0 = pose / small, 1 = shape / large, 2 = expression / large; None = not part of this module),
+    re-packed whenever a parameter / buffer is modified or moved, and the raw forward through the C ABI.
 
-    def init_weights(self):                     # smirk_encoder.py:26-31
-        self.pose_cam_layers[-1].weight.data *= 0.001
-        self.pose_cam_layers[-1].bias.data *= 0.001
-        self.pose_cam_layers[-1].weight.data[3] = 0
-        self.pose_cam_layers[-1].bias.data[3] = 7
+    ``precision``: 0 fp32 CUDA cores | 1 TF32 tcgen05 1x1 convs | 2 = 1 + fused expand/depthwise blocks |
+    3 = 2 with error-compensated 3xTF32 arithmetic (fp32-equivalent; the parity path)."""
 
-
-class ShapeEncoder(nn.Module):
-    def __init__(self, n_shape=300):
-        super().__init__()
-        self.encoder, feature_dim = create_backbone("tf_mobilenetv3_large_minimal_100")
-        self.shape_layers = nn.Sequential(nn.Linear(feature_dim, n_shape))
-        self.init_weights()
-
-    def init_weights(self):                     # smirk_encoder.py:61-63
-        self.shape_layers[-1].weight.data *= 0
-        self.shape_layers[-1].bias.data *= 0
-
-
-class ExpressionEncoder(nn.Module):
-    def __init__(self, n_exp=50):
-        super().__init__()
-        self.encoder, feature_dim = create_backbone("tf_mobilenetv3_large_minimal_100")
-        self.expression_layers = nn.Sequential(nn.Linear(feature_dim, n_exp + 2 + 3))
-        self.n_exp = n_exp
-        self.init_weights()
-
-    def init_weights(self):                     # smirk_encoder.py:90-92
-        self.expression_layers[-1].weight.data *= 0.1
-        self.expression_layers[-1].bias.data *= 0.1
-
-
-class SmirkEncoder(nn.Module):
-    def __init__(self, n_exp=50, n_shape=300):
-        super().__init__()
-        self.pose_encoder = PoseEncoder()
-        self.shape_encoder = ShapeEncoder(n_shape=n_shape)
-        self.expression_encoder = ExpressionEncoder(n_exp=n_exp)
+    def _init_native(self, n_exp=50, n_shape=300):
         self.n_exp, self.n_shape = n_exp, n_shape
         self.precision = 0
         self._handle, self._sig, self._ws = None, None, _lib.Workspace()
 
-    # -- native handle (re-packed whenever a parameter / buffer is modified or moved) ----------------
-    def _signature(self, device):
-        s = [str(device), self.precision]
-        for t in list(self.parameters()) + list(self.buffers()):
-            s.append(t._version)
-            s.append(t.data_ptr())
-        return tuple(s)
+    def _parts(self):
+        raise NotImplementedError
 
     def _native(self, device):
-        sig = self._signature(device)
+        sig = _lib.buffers_signature(self, device, self.precision)
         if self._handle is not None and self._sig == sig:
             return self._handle
         self._release()
-        if self.training:
-            raise RuntimeError("smirk_b200.SmirkEncoder: train-mode BatchNorm is not implemented (forward/eval only)")
         L = _lib.lib()
         keep = []
         d = _lib.SmkEncoderDesc()
-        heads = (self.pose_encoder.pose_cam_layers[0], self.shape_encoder.shape_layers[0],
-                 self.expression_encoder.expression_layers[0])
-        for i, enc in enumerate((self.pose_encoder, self.shape_encoder, self.expression_encoder)):
+        for i, part in enumerate(self._parts()):
+            if part is None:
+                d.n_tensors[i] = 0
+                continue
+            enc, head = part
             ts = enc.encoder.tensor_list()
             arr = (_lib.c_f32p * len(ts))()
             for j, t in enumerate(ts):
@@ -186,25 +145,17 @@ class SmirkEncoder(nn.Module):
             keep.append(arr)
             d.tensors[i] = C.cast(arr, C.POINTER(_lib.c_f32p))
             d.n_tensors[i] = len(ts)
-            a, p = _lib.f32(heads[i].weight); keep.append(a); d.head_w[i] = p
-            a, p = _lib.f32(heads[i].bias); keep.append(a); d.head_b[i] = p
-        d.n_shape, d.n_exp, d.precision = self.n_shape, self.n_exp, self.precision
+            a, p = _lib.f32(head.weight); keep.append(a); d.head_w[i] = p
+            a, p = _lib.f32(head.bias); keep.append(a); d.head_b[i] = p
+        d.n_shape, d.n_exp, d.precision = self.n_shape, self.n_exp, int(self.precision)
         h = C.c_void_p()
         with torch.cuda.device(device):
             _lib.check(L.smk_encoder_create(C.byref(d), C.byref(h)), "smk_encoder_create")
-        self._handle, self._sig = h, sig
-        return h
+        self._handle, self._sig = _lib.NativeHandle(h, "smk_encoder_destroy"), sig
+        return self._handle
 
     def _release(self):
-        if getattr(self, "_handle", None) is not None:
-            try:
-                _lib.lib().smk_encoder_destroy(self._handle)
-            except Exception:
-                pass
-            self._handle = None
-
-    def __del__(self):
-        self._release()
+        self._handle = None                    # the native object dies with its last reference (_lib.NativeHandle)
 
     def __deepcopy__(self, memo):               # base_trainer.py:237 deep-copies the encoder
         import copy
@@ -217,21 +168,105 @@ class SmirkEncoder(nn.Module):
         return new
 
     @torch.no_grad()
-    def forward(self, img):
+    def _run(self, img):
+        """img [B,3,224,224] -> (pose_cam [B,6] | None, shape [B,n_shape] | None, expr [B,n_exp+5] | None)."""
         _lib.require_cuda(img, "img")
+        if self.training:                      # checked on every call: .train() after the first forward must not silently run eval BN
+            raise RuntimeError("smirk_b200.%s: train-mode BatchNorm is not implemented (forward/eval only)" % type(self).__name__)
         dev = img.device
         L = _lib.lib()
         h = self._native(dev)
         x = _lib.dev_f32(img, "img")
         if x.dim() != 4 or tuple(x.shape[1:]) != (3, 224, 224):
-            raise RuntimeError("smirk_b200.SmirkEncoder: expected img [B,3,224,224], got %s" % (tuple(x.shape),))
-        B, ne = x.shape[0], self.n_exp
-        o = lambda n: torch.empty(B, n, dtype=torch.float32, device=dev)
-        pose_cam, shape, expr = o(6), o(self.n_shape), o(ne + 5)
+            raise RuntimeError("smirk_b200.%s: expected img [B,3,224,224], got %s" % (type(self).__name__, tuple(x.shape)))
+        B = x.shape[0]
+        widths = (6, self.n_shape, self.n_exp + 5)
+        outs = [torch.empty(B, w, dtype=torch.float32, device=dev) if part is not None else None
+                for w, part in zip(widths, self._parts())]
         with torch.cuda.device(dev):
             ws = self._ws.get(L.smk_encoder_workspace_bytes(h, B), dev)
-            _lib.check(L.smk_encoder_forward(h, _lib.ptr(x), B, _lib.ptr(pose_cam), _lib.ptr(shape), _lib.ptr(expr),
+            _lib.check(L.smk_encoder_forward(h, _lib.ptr(x), B, _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]),
                                              _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "smk_encoder_forward")
+        return outs
+
+
+class PoseEncoder(_NativeEncoder):
+    def __init__(self):
+        super().__init__()
+        self.encoder, feature_dim = create_backbone("tf_mobilenetv3_small_minimal_100")
+        self.pose_cam_layers = nn.Sequential(nn.Linear(feature_dim, 6))
+        self._init_native()
+        self.init_weights()
+
+    def init_weights(self):                     # smirk_encoder.py:26-31
+        self.pose_cam_layers[-1].weight.data *= 0.001
+        self.pose_cam_layers[-1].bias.data *= 0.001
+        self.pose_cam_layers[-1].weight.data[3] = 0
+        self.pose_cam_layers[-1].bias.data[3] = 7
+
+    def _parts(self):
+        return ((self, self.pose_cam_layers[0]), None, None)
+
+    def forward(self, img):                     # smirk_encoder.py:34-45
+        pose_cam = self._run(img)[0]
+        return {"pose_params": pose_cam[..., :3], "cam": pose_cam[..., 3:]}
+
+
+class ShapeEncoder(_NativeEncoder):
+    def __init__(self, n_shape=300):
+        super().__init__()
+        self.encoder, feature_dim = create_backbone("tf_mobilenetv3_large_minimal_100")
+        self.shape_layers = nn.Sequential(nn.Linear(feature_dim, n_shape))
+        self._init_native(n_shape=n_shape)
+        self.init_weights()
+
+    def init_weights(self):                     # smirk_encoder.py:61-63
+        self.shape_layers[-1].weight.data *= 0
+        self.shape_layers[-1].bias.data *= 0
+
+    def _parts(self):
+        return (None, (self, self.shape_layers[0]), None)
+
+    def forward(self, img):                     # smirk_encoder.py:66-73
+        return {"shape_params": self._run(img)[1]}
+
+
+class ExpressionEncoder(_NativeEncoder):
+    def __init__(self, n_exp=50):
+        super().__init__()
+        self.encoder, feature_dim = create_backbone("tf_mobilenetv3_large_minimal_100")
+        self.expression_layers = nn.Sequential(nn.Linear(feature_dim, n_exp + 2 + 3))
+        self._init_native(n_exp=n_exp)
+        self.init_weights()
+
+    def init_weights(self):                     # smirk_encoder.py:90-92
+        self.expression_layers[-1].weight.data *= 0.1
+        self.expression_layers[-1].bias.data *= 0.1
+
+    def _parts(self):
+        return (None, None, (self, self.expression_layers[0]))
+
+    def forward(self, img):                     # smirk_encoder.py:95-110 (clamps applied by the native head kernel)
+        expr, ne = self._run(img)[2], self.n_exp
+        return {"expression_params": expr[..., :ne], "eyelid_params": expr[..., ne:ne + 2], "jaw_params": expr[..., ne + 2:ne + 5]}
+
+
+class SmirkEncoder(_NativeEncoder):
+    def __init__(self, n_exp=50, n_shape=300):
+        super().__init__()
+        self.pose_encoder = PoseEncoder()
+        self.shape_encoder = ShapeEncoder(n_shape=n_shape)
+        self.expression_encoder = ExpressionEncoder(n_exp=n_exp)
+        self._init_native(n_exp=n_exp, n_shape=n_shape)
+
+    def _parts(self):
+        return ((self.pose_encoder, self.pose_encoder.pose_cam_layers[0]),
+                (self.shape_encoder, self.shape_encoder.shape_layers[0]),
+                (self.expression_encoder, self.expression_encoder.expression_layers[0]))
+
+    def forward(self, img):                     # smirk_encoder.py:123-133: one native call runs the three backbones concurrently
+        pose_cam, shape, expr = self._run(img)
+        ne = self.n_exp
         return {
             "pose_params": pose_cam[..., :3], "cam": pose_cam[..., 3:],
             "shape_params": shape,

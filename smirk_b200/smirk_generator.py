@@ -75,8 +75,6 @@ class SmirkGenerator(nn.Module):
         if self._handle is not None and self._sig == sig:
             return self._handle
         self._release()
-        if self.training:
-            raise RuntimeError("smirk_b200.SmirkGenerator: train-mode BatchNorm is not implemented (forward/eval only)")
         L = _lib.lib()
         keep = []
         ts = [v for k, v in self.state_dict().items() if not k.endswith("num_batches_tracked")]
@@ -91,19 +89,11 @@ class SmirkGenerator(nn.Module):
         h = C.c_void_p()
         with torch.cuda.device(device):
             _lib.check(L.smk_generator_create(C.byref(d), C.byref(h)), "smk_generator_create")
-        self._handle, self._sig = h, sig
-        return h
+        self._handle, self._sig = _lib.NativeHandle(h, "smk_generator_destroy"), sig
+        return self._handle
 
     def _release(self):
-        if getattr(self, "_handle", None) is not None:
-            try:
-                _lib.lib().smk_generator_destroy(self._handle)
-            except Exception:
-                pass
-            self._handle = None
-
-    def __del__(self):
-        self._release()
+        self._handle = None                    # the native object dies with its last reference (_lib.NativeHandle)
 
     def __deepcopy__(self, memo):
         import copy
@@ -118,6 +108,8 @@ class SmirkGenerator(nn.Module):
     @torch.no_grad()
     def forward(self, x):
         _lib.require_cuda(x, "x")
+        if self.training:                      # checked on every call: .train() after the first forward must not silently run eval BN
+            raise RuntimeError("smirk_b200.SmirkGenerator: train-mode BatchNorm is not implemented (forward/eval only)")
         dev = x.device
         L = _lib.lib()
         h = self._native(dev)

@@ -272,3 +272,67 @@ def test_stem_ds_fused_kernel(native_lib, B, H, stride):
     assert torch.isfinite(got).all(), "unwritten outputs: %d" % int((~torch.isfinite(got)).sum())
     err = (got - ref).abs().max().item()
     assert err <= 1e-4 * ref.abs().max().item(), "max err %.3g vs scale %.3g" % (err, ref.abs().max().item())
+
+
+# ----------------------------------------------------------------- 3xTF32 error-compensated variants (encoder precision 3)
+def tf32_split(w):
+    """hi = tf32(w) (round to nearest, ties away — cvt.rna), lo = tf32(w - hi): what smk_encoder_create packs."""
+    def rna(t):
+        u = t.contiguous().view(torch.int32)
+        r = ((u + 0x1000) & ~0x1FFF).view(torch.float32)
+        return r
+    hi = rna(w)
+    return hi, rna(w - hi)
+
+
+@pytest.mark.parametrize("M,K,N,relu,use_res", [
+    (6272, 184, 80, 0, 1),       # 14x14 projection with residual: ragged K (5.75 k-blocks), ragged N tile
+    (1568, 960, 160, 0, 0),      # 7x7, deep K
+    (100352, 16, 16, 0, 1),      # 112^2 x 8 images, K < one k-block
+    (1000, 96, 576, 1, 0),       # M not a multiple of 128, wide N (cn layer)
+])
+def test_gemm_tc3x_matches_fp64(native_lib, M, K, N, relu, use_res):
+    g = torch.Generator().manual_seed(61)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    scale, bias = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g) * 0.1
+    res = torch.randn(M, N, generator=g) if use_res else None
+    ref = (a.double() @ w.double().t()) * scale.double() + bias.double()
+    if res is not None:
+        ref = ref + res.double()
+    ref = (F.relu(ref) if relu else ref).float()
+    hi, lo = tf32_split(w)
+    d = [t.to(DEV) if t is not None else None for t in (a, hi, lo, scale, bias, res)]
+    out = torch.full((M, N), float("nan"), device=DEV)
+    rc = native_lib.smk_debug_gemm_tc3x(P(d[0]), K, M, P(d[1]), P(d[2]), P(d[3]), P(d[4]), N, K, relu, P(d[5]), N, P(out), N, stream())
+    assert rc == 0, native_lib.smk_last_error()
+    torch.cuda.synchronize()
+    got = out.cpu()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-6 * ref.abs().max().item() * max(1.0, (K / 64) ** 0.5), "max err %.3g vs scale %.3g" % (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,H,Cin,mid,stride", [(2, 28, 40, 120, 1), (1, 14, 80, 200, 1), (3, 56, 24, 72, 2), (1, 112, 16, 64, 2), (2, 14, 112, 672, 1)])
+def test_xdw3x_matches_fp64(native_lib, B, H, Cin, mid, stride):
+    g = torch.Generator().manual_seed(62)
+    x = torch.randn(B, Cin, H, H, generator=g)
+    w1 = torch.randn(mid, Cin, 1, 1, generator=g) / Cin ** 0.5
+    s1, b1 = torch.rand(mid, generator=g) + 0.5, torch.randn(mid, generator=g) * 0.2
+    wd = torch.randn(mid, 1, 3, 3, generator=g) / 3.0
+    s2, b2 = torch.rand(mid, generator=g) + 0.5, torch.randn(mid, generator=g) * 0.2
+    dd = torch.float64
+    e = F.relu(F.conv2d(x.to(dd), w1.to(dd)) * s1.to(dd).view(1, -1, 1, 1) + b1.to(dd).view(1, -1, 1, 1))
+    ref = F.relu(tf_same_dw(e, wd.to(dd), stride) * s2.to(dd).view(1, -1, 1, 1) + b2.to(dd).view(1, -1, 1, 1)).float()
+    Ho = (H + stride - 1) // stride
+    hi, lo = tf32_split(w1.view(mid, Cin))
+    xd, wdd = nhwc(x).to(DEV), wd.view(mid, 9).t().contiguous().to(DEV)
+    t = [hi.to(DEV), lo.to(DEV), s1.to(DEV), b1.to(DEV), s2.to(DEV), b2.to(DEV)]
+    out = torch.full((B, Ho, Ho, mid), float("nan"), device=DEV)
+    rc = native_lib.smk_debug_xdw3x(P(xd), B, H, H, Cin, P(t[0]), P(t[1]), P(t[2]), P(t[3]), mid, P(wdd), P(t[4]), P(t[5]), stride, P(out), stream())
+    assert rc == 0, native_lib.smk_last_error()
+    torch.cuda.synchronize()
+    got = out.permute(0, 3, 1, 2).cpu()
+    assert torch.isfinite(got).all(), "unwritten outputs: %d" % int((~torch.isfinite(got)).sum())
+    err = (got - ref).abs().max().item()
+    assert err <= 5e-6 * ref.abs().max().item(), "max err %.3g vs scale %.3g" % (err, ref.abs().max().item())

