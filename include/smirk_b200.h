@@ -175,7 +175,6 @@ int smk_f32chw_to_u8hwc(const float* in, int B, int S, uint8_t* out, void* strea
 
 /* ------------------------------------------------------------------------------------------------
  * Masking between Renderer and SmirkGenerator (src/utils/masking.py, demo.py:138-167).
- * WORK IN PROGRESS (branch wip/masking-kernels): not yet validated on a GPU.
  * Random draws stay with the caller (torch); these entry points are the deterministic parts.
  *   face_weights: trans_verts [B,V,3], base_prob [F] -> weights [B,F]               (masking.py:146-160)
  *   points      : face_idx int64 [B,N], bary [B,N,3] -> npoints int64 [B,N,2] (x,y)  (masking.py:166-174)
@@ -193,6 +192,20 @@ int smk_masking_points(const SmkMasking* h, const float* trans_verts, const int6
 int smk_masking_compose(const SmkMasking* h, const float* img, const float* hull, const int64_t* npoints, const int64_t* rbound,
                         int N, const float* rendered_mask, const float* noise_mult, const float* random_centres,
                         int wr, int B, int S, float* masked, void* ws, size_t ws_bytes, void* stream);
+/* The whole step of demo.py:138-165 with the random draws made on the device (Philox4x32-10, keyed by rng_state[0] = seed
+ * and rng_state[1] = call counter, which the call increments on the stream — graph replays draw fresh samples):
+ *   face weights -> N = int(mask_ratio * ratio_mul * S * S) faces by inverse CDF (multinomial with replacement) -> uniform
+ *   barycentrics -> pixel coordinates -> per-image budget rbound = N / ratio_mul * U(1, ratio_mul)^(+-1) -> point mask ->
+ *   masking(img, hull, img * pmask, wr, rendered_mask = any(rendered != 0), extra_noise, random_mask = p_centre).
+ * rendered [B,3,S,S] is the Renderer's output; hull [B,1,S,S] the landmark hull mask (1 outside the face).  Optional
+ * debug outputs (NULL to skip) export the draws so the result can be checked against the reference's functions:
+ * dbg_face_idx int64 [B,N], dbg_bary [B,N,3], dbg_npoints int64 [B,N,2], dbg_rbound int64 [B], dbg_noise [B,3,S,S],
+ * dbg_centres [B,1,S,S].  ws >= smk_masking_forward_workspace_bytes(h, B, S, N).                                          */
+size_t smk_masking_forward_workspace_bytes(const SmkMasking* h, int B, int S, int N);
+int smk_masking_forward(const SmkMasking* h, const float* img, const float* hull, const float* trans_verts, const float* rendered,
+                        const float* base_prob, int B, int S, int N, int wr, float ratio_mul, float p_centre, int extra_noise,
+                        uint64_t* rng_state, float* masked, int64_t* dbg_face_idx, float* dbg_bary, int64_t* dbg_npoints,
+                        int64_t* dbg_rbound, float* dbg_noise, float* dbg_centres, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Kernel-level test entry points (used by tests/ to check single convolution kernels against torch;

@@ -54,7 +54,7 @@ struct TcArgs {
     int round_out;                 // 1: round the stored activations to TF32 (round-to-nearest) for the next tensor-core layer
 };
 
-template <int BN, int STAGES, int MINB, bool PERSIST, bool X3>
+template <int BN, int STAGES, int MINB, bool PERSIST, int X3>
 __global__ void __launch_bounds__(NUM_THREADS, MINB)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const TcArgs a) {
@@ -72,11 +72,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     //                    memory by the epilogue warps, which are otherwise idle during the main loop of a single-tile
     //                    CTA: they rewrite the landed A tile with its heads (so the tensor core sees exact TF32 words
     //                    whatever it does with the low mantissa bits) and write the tails to a second tile.
+    //                    X3 = 1 keeps the tails in shared memory (stage = [A][B][A_lo][B_lo]); X3 = 2 parks them in TENSOR
+    //                    MEMORY instead (32 columns per stage next to the accumulator) and multiplies them with the
+    //                    A-from-TMEM form of tcgen05.mma: the shared-memory footprint stays that of the plain TF32 kernel
+    //                    plus the weight tails, so as many CTAs share an SM as before — which is what the concurrent
+    //                    pipeline's throughput hangs on (DESIGN.md "footprint beats per-kernel speed").
     static_assert(!X3 || !PERSIST, "the 3xTF32 split borrows the epilogue warps: single-tile CTAs only");
     constexpr int B_STAGE_BYTES = BN * BKB;
     constexpr int HALF_STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    constexpr int STAGE_BYTES = (X3 ? 2 : 1) * HALF_STAGE_BYTES;
-    constexpr uint32_t TMEM_COLS = PERSIST ? 2 * BN : BN;   // 32..256: powers of two
+    constexpr int STAGE_BYTES = X3 == 1 ? 2 * HALF_STAGE_BYTES : (X3 == 2 ? HALF_STAGE_BYTES + B_STAGE_BYTES : HALF_STAGE_BYTES);
+    constexpr int BLO_OFF = X3 == 1 ? HALF_STAGE_BYTES + A_STAGE_BYTES : HALF_STAGE_BYTES;      // weight tails within a stage
+    constexpr uint32_t ALO_COL = PERSIST ? 2 * BN : BN;                                            // X3 == 2: first TMEM column of the A tails
+    constexpr uint32_t TMEM_NEED = (PERSIST ? 2 * BN : BN) + (X3 == 2 ? STAGES * 32 : 0);
+    constexpr uint32_t TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
     constexpr uint32_t IDESC = make_idesc(BM, BN);
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B; offset arithmetic keeps the shared address space visible to the
@@ -125,7 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint8_t* sa = smem + s * STAGE_BYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
                     mbar_expect_tx(&full[s], (uint32_t)(HALF_STAGE_BYTES + (X3 ? B_STAGE_BYTES : 0)));
-                    if (X3) tma_load_2d(&tmBlo, sa + HALF_STAGE_BYTES + A_STAGE_BYTES, &full[s], kb * BK, n0);
+                    if (X3) tma_load_2d(&tmBlo, sa + BLO_OFF, &full[s], kb * BK, n0);
                     if (a.mode == 0) {
                         tma_load_2d(&tmA, sa, &full[s], kb * BK, m0);
                     } else {
@@ -157,9 +165,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         uint64_t db = make_smem_desc(sb + k * UMMA_K * 4);
                         umma_tf32(tmem_base + (uint32_t)(buf * BN), da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
                         if (X3) {
-                            uint64_t dal = make_smem_desc(sa + HALF_STAGE_BYTES + k * UMMA_K * 4);
-                            uint64_t dbl = make_smem_desc(sb + HALF_STAGE_BYTES + k * UMMA_K * 4);
-                            umma_tf32(tmem_base + (uint32_t)(buf * BN), dal, db, IDESC, 1u);      // a_lo * w_hi
+                            uint64_t dbl = make_smem_desc(sa + BLO_OFF + k * UMMA_K * 4);
+                            if (X3 == 1) umma_tf32(tmem_base + (uint32_t)(buf * BN), make_smem_desc(sa + HALF_STAGE_BYTES + k * UMMA_K * 4), db, IDESC, 1u);   // a_lo * w_hi
+                            else umma_tf32_ts(tmem_base + (uint32_t)(buf * BN), tmem_base + ALO_COL + (uint32_t)(s * 32 + k * UMMA_K), db, IDESC, 1u);
                             umma_tf32(tmem_base + (uint32_t)(buf * BN), da, dbl, IDESC, 1u);      // a_hi * w_lo
                         }
                     }
@@ -178,7 +186,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         //      scale/bias (+residual) (+ReLU) (+TF32 rounding) and store — every global access of the
         //      warp now covers whole 128-byte lines of 4 output rows instead of 16 bytes of 32 rows.
         const int quarter = warp & 3;
-        if (X3) {
+        if (X3 == 2) {
+            // ===== 3xTF32, tails in tensor memory: thread = tile row (its TMEM lane); heads rewritten in place =====
+            const int r = quarter * 32 + lane;
+            for (int kb = 0; kb < a.nkb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&full[s], (uint32_t)(kb / STAGES) & 1u);
+                uint8_t* row = smem + s * STAGE_BYTES + r * 128;
+                float lo[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4* p = reinterpret_cast<float4*>(row + ((j ^ (r & 7)) << 4));       // 16-byte chunk j of the row (SWIZZLE_128B)
+                    const float4 v = *p;
+                    float4 hi;
+                    hi.x = smk::round_tf32(v.x); hi.y = smk::round_tf32(v.y); hi.z = smk::round_tf32(v.z); hi.w = smk::round_tf32(v.w);
+                    lo[4 * j] = v.x - hi.x; lo[4 * j + 1] = v.y - hi.y; lo[4 * j + 2] = v.z - hi.z; lo[4 * j + 3] = v.w - hi.w;
+                    *p = hi;
+                }
+                tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ALO_COL + (uint32_t)(s * 32), lo);   // warp-collective, waits for completion
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&split[s]);
+            }
+            tcgen05_fence_after();
+        } else if (X3 == 1) {
             // ===== 3xTF32: split every landed A tile into TF32 heads (in place) and tails (second tile) =====
             const int t = threadIdx.x - 64;                        // 0..127
             for (int kb = 0; kb < a.nkb; ++kb) {
@@ -351,11 +383,12 @@ int encode_im2col(CUtensorMap* map, const float* base, int B, int Hin, int Win, 
     return 0;
 }
 
-template <int BN, int STAGES, int MINB, bool PERSIST, bool X3 = false>
+template <int BN, int STAGES, int MINB, bool PERSIST, int X3 = 0>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a_in, cudaStream_t st, const CUtensorMap* tmBlo = nullptr) {
-    constexpr size_t smem = (size_t)STAGES * (X3 ? 2 : 1) * (A_STAGE_BYTES + BN * BKB) + (PERSIST ? SLAB_BYTES : 0) + 1024 + 256;
+    constexpr size_t stage = X3 == 1 ? 2 * (A_STAGE_BYTES + BN * BKB) : (X3 == 2 ? A_STAGE_BYTES + 2 * BN * BKB : A_STAGE_BYTES + BN * BKB);
+    constexpr size_t smem = (size_t)STAGES * stage + (PERSIST ? SLAB_BYTES : 0) + 1024 + 256;
     static_assert(MINB * (smem + 1024) <= 228 * 1024, "shared memory budget of MINB resident CTAs");
-    static_assert(MINB * (PERSIST ? 2 : 1) * BN <= 512, "TMEM budget of MINB resident CTAs");
+    static_assert(MINB * ((PERSIST ? 2 : 1) * BN + (X3 == 2 ? STAGES * 32 : 0)) <= 512, "TMEM budget of MINB resident CTAs");
     // The attribute is per device and per function; set it once per (device, instantiation).  One bit per
     // device ordinal; a benign race (two threads setting it twice) is harmless.
     static unsigned long long configured_mask = 0;
@@ -426,9 +459,16 @@ int tc_conv(const TcConv& p, cudaStream_t st) {
         SMK_REQUIRE(p.mode == 0 && p.store == 0, "tc_conv: the 3xTF32 path covers plain 1x1 convolutions / GEMMs");
         CUtensorMap tmBlo;
         if (int rc = encode_2d(&tmBlo, p.wt_lo, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, (uint32_t)BN)) return rc;
-        if (BN == 32) return launch<32, 2, 2, false, true>(tmA, tmB, a, st, &tmBlo);
-        if (BN == 64) return launch<64, 2, 2, false, true>(tmA, tmB, a, st, &tmBlo);
-        return launch<128, 2, 1, false, true>(tmA, tmB, a, st, &tmBlo);
+        // tails of the activations in tensor memory (default) or in shared memory (SMK_X3_TMEM=0: the first, larger-footprint cut)
+        static const int x3_tmem = []() { const char* e = getenv("SMK_X3_TMEM"); return e ? atoi(e) : 1; }();
+        if (x3_tmem) {
+            if (BN == 32) return launch<32, 2, 4, false, 2>(tmA, tmB, a, st, &tmBlo);
+            if (BN == 64) return launch<64, 2, 3, false, 2>(tmA, tmB, a, st, &tmBlo);
+            return launch<128, 2, 2, false, 2>(tmA, tmB, a, st, &tmBlo);
+        }
+        if (BN == 32) return launch<32, 2, 2, false, 1>(tmA, tmB, a, st, &tmBlo);
+        if (BN == 64) return launch<64, 2, 2, false, 1>(tmA, tmB, a, st, &tmBlo);
+        return launch<128, 2, 1, false, 1>(tmA, tmB, a, st, &tmBlo);
     }
     if (deep_small && BN == 32) return launch<32, 8, 1, false>(tmA, tmB, a, st);
     if (deep_small && BN == 64) return launch<64, 8, 1, false>(tmA, tmB, a, st);

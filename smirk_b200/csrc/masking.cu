@@ -12,6 +12,13 @@
 //                              (1 - maxpool(1 - mask)), x (1 - rendered_mask), noise on the retained points, 11x11
 //                              patches knocked out around random centres, composite — three launches, two of them the
 //                              separable halves of the max-pools.
+// (2) smk_masking_forward chains them into the whole demo.py:138-165 step with the draws made ON the device by a
+// counter-based generator (Philox4x32-10 keyed by (seed, counter, element)): multinomial face sampling by inverse CDF,
+// uniform barycentrics, the per-image point budget `rbound`, the Gaussian pixel noise and the Bernoulli patch centres.
+// The reference draws from torch's global RNG, so only distributional parity with it is possible;
+// what IS exact: given the draws this call exports (optional debug outputs), the masked image equals the reference's
+// `masking()` fed the same draws.  The counter lives in device memory and is advanced by the last kernel, so a captured
+// CUDA graph produces fresh draws on every replay.
 // All of it is HBM-bound byte/float shuffling over [B,3,224,224] images (602 KB per face in, 602 KB out).
 #include "common.cuh"
 #include <math.h>
@@ -162,6 +169,105 @@ mask_compose_kernel(const float* __restrict__ img, const float* __restrict__ th,
     }
 }
 
+
+// ---- counter-based RNG: Philox4x32-10 (Salmon et al. 2011), key = seed, counter = (element, stream, call counter) ----
+struct U4 { uint32_t x, y, z, w; };
+__device__ __forceinline__ U4 philox(uint64_t seed, uint64_t ctr, uint32_t stream, uint32_t elem_hi, uint32_t elem_lo) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    U4 c{elem_lo, elem_hi, (uint32_t)ctr ^ (stream << 28), (uint32_t)(ctr >> 32)};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = U4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }          // [0, 1)
+
+// one CTA per image: inclusive CDF of the face weights in shared memory, N inverse-CDF samples, barycentrics, rbound
+__global__ void __launch_bounds__(512)
+mask_sample_kernel(const float* __restrict__ w, int F, int N, float ratio_mul, const uint64_t* __restrict__ rng,
+                   int64_t* __restrict__ fidx, float* __restrict__ bary, int64_t* __restrict__ rbound) {
+    smk::pdl_sync();
+    extern __shared__ float cdf[];                      // [F]
+    __shared__ float part[512];
+    const int b = blockIdx.x, t = threadIdx.x, nt = blockDim.x;
+    const float* wb = w + (size_t)b * F;
+    const int per = (F + nt - 1) / nt, lo = t * per, hi = min(F, lo + per);
+    float s = 0.f;
+    for (int i = lo; i < hi; ++i) { s += fmaxf(wb[i], 0.f); cdf[i] = s; }
+    part[t] = s;
+    __syncthreads();
+    for (int off = 1; off < nt; off <<= 1) {            // Hillis-Steele scan of the per-thread totals
+        float v = t >= off ? part[t - off] : 0.f;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    const float base = t > 0 ? part[t - 1] : 0.f;
+    for (int i = lo; i < hi; ++i) cdf[i] += base;
+    __syncthreads();
+    const float total = part[nt - 1];
+    const uint64_t seed = rng[0], ctr = rng[1];
+    for (int j = t; j < N; j += nt) {
+        const U4 r = philox(seed, ctr, 0u, (uint32_t)b, (uint32_t)j);
+        int f = 0;
+        if (total > 0.f) {
+            const float x = u01(r.x) * total;
+            int a = 0, c = F - 1;                       // first index with cdf > x
+            while (a < c) { const int m = (a + c) >> 1; if (cdf[m] > x) c = m; else a = m + 1; }
+            f = a;
+        }
+        float u = u01(r.y), v = u01(r.z);
+        if (u + v > 1.f) { u = 1.f - u; v = 1.f - v; }  // masking.py:61-66: reflect into the triangle
+        const size_t o = (size_t)b * N + j;
+        fidx[o] = f;
+        bary[o * 3] = 1.f - (u + v); bary[o * 3 + 1] = u; bary[o * 3 + 2] = v;
+    }
+    if (t == 0) {                                       // demo.py:151-153
+        const U4 r = philox(seed, ctr, 1u, (uint32_t)b, 0u);
+        const float rsign = (r.x & 1u) ? 1.f : -1.f;
+        const float rscale = u01(r.y) * (ratio_mul - 1.f) + 1.f;
+        rbound[b] = (int64_t)((float)N * (1.f / ratio_mul) * powf(rscale, rsign));
+    }
+}
+
+// noise_mult[b,c,y,x] = N(0,1) * 0.05 + 1 (masking.py:84-86); centres[b,0,y,x] ~ Bernoulli(p) (masking.py:89-92)
+__global__ void __launch_bounds__(256)
+mask_rng_fill_kernel(int B, int S, float p_centre, const uint64_t* __restrict__ rng, float* __restrict__ noise, float* __restrict__ centres) {
+    smk::pdl_sync();
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long npx = (long)B * S * S;
+    if (i >= npx) return;
+    const uint64_t seed = rng[0], ctr = rng[1];
+    const U4 r = philox(seed, ctr, 2u, (uint32_t)(i >> 32), (uint32_t)i);
+    const U4 q = philox(seed, ctr, 3u, (uint32_t)(i >> 32), (uint32_t)i);
+    const int b = (int)(i / ((long)S * S)); const long pix = i - (long)b * S * S;
+    // Box-Muller: two uniforms -> two normals; three channels use (r.x,r.y) cos / sin and (r.z,r.w) cos
+    const float m0 = sqrtf(-2.f * logf(1.f - u01(r.x))), a0 = 6.2831853f * u01(r.y);
+    const float m1 = sqrtf(-2.f * logf(1.f - u01(r.z))), a1 = 6.2831853f * u01(r.w);
+    const float n[3] = {m0 * cosf(a0), m0 * sinf(a0), m1 * cosf(a1)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) noise[((size_t)b * 3 + c) * S * S + pix] = fmaf(n[c], 0.05f, 1.0f);
+    centres[i] = u01(q.x) < p_centre ? 1.f : 0.f;
+}
+
+// rendered_mask = 1 - all(rendered == 0 over channels)   (demo.py:146)
+__global__ void __launch_bounds__(256)
+mask_rendered_kernel(const float* __restrict__ rendered, int B, int S, float* __restrict__ rmask) {
+    smk::pdl_sync();
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)B * S * S) return;
+    const int b = (int)(i / ((long)S * S)); const long pix = i - (long)b * S * S;
+    const float* r = rendered + (size_t)b * 3 * S * S + pix;
+    const bool bg = r[0] == 0.f && r[(size_t)S * S] == 0.f && r[(size_t)2 * S * S] == 0.f;
+    rmask[i] = bg ? 0.f : 1.f;
+}
+
+__global__ void mask_rng_advance_kernel(uint64_t* rng) { smk::pdl_sync(); if (threadIdx.x == 0) rng[1] += 1; }
+
 }  // namespace
 
 struct SmkMasking {
@@ -253,6 +359,64 @@ extern "C" int smk_masking_compose(const SmkMasking* h, const float* img, const 
     SMK_TAG("mask_compose", 4.0 * npx * (3 + 3 + 2 + (noise_mult ? 3 : 0)), 0.0, st);
     SMK_LAUNCH(mask_compose_kernel, dim3(smk::cdiv(npx, 256)), dim3(256), 0, st, img, (const float*)th, (const float*)(random_centres ? tc : nullptr),
                (const uint8_t*)pm, rendered_mask, noise_mult, B, S, wr, masked);
+    SMK_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" size_t smk_masking_forward_workspace_bytes(const SmkMasking* h, int B, int S, int N) {
+    const size_t b = (size_t)(B > 0 ? B : 1), px = b * S * S;
+    return smk_masking_workspace_bytes(h, B, S) + smk::ws_round(b * h->d.F * sizeof(float)) + smk::ws_round(b * N * 8) + smk::ws_round(b * N * 12) +
+           smk::ws_round(b * N * 16) + smk::ws_round(b * 8) + smk::ws_round(px * 12) + 2 * smk::ws_round(px * 4) + 4096;
+}
+
+extern "C" int smk_masking_forward(const SmkMasking* h, const float* img, const float* hull, const float* trans_verts, const float* rendered,
+                                   const float* base_prob, int B, int S, int N, int wr, float ratio_mul, float p_centre, int extra_noise,
+                                   uint64_t* rng_state, float* masked, int64_t* dbg_face_idx, float* dbg_bary, int64_t* dbg_npoints,
+                                   int64_t* dbg_rbound, float* dbg_noise, float* dbg_centres, void* ws, size_t ws_bytes, void* stream) {
+    if (B == 0) return 0;
+    SMK_REQUIRE(h && img && hull && trans_verts && rendered && base_prob && rng_state && masked, "smk_masking_forward: null argument");
+    SMK_REQUIRE(N > 0 && S > 0 && wr >= 0 && ratio_mul >= 1.f, "smk_masking_forward: bad sizes");
+    SMK_REQUIRE(ws && ws_bytes >= smk_masking_forward_workspace_bytes(h, B, S, N), "smk_masking_forward: workspace too small");
+    SMK_REQUIRE((size_t)h->d.F * sizeof(float) <= 160 * 1024, "smk_masking_forward: too many faces for the shared-memory CDF");
+    cudaStream_t st = (cudaStream_t)stream;
+    const MaskDev& d = h->d;
+    const size_t base = smk_masking_workspace_bytes(h, B, S);
+    smk::Workspace w((char*)ws + base, ws_bytes - base);
+    const long npx = (long)B * S * S;
+    float* weights = w.take<float>((size_t)B * d.F);
+    int64_t* fidx = dbg_face_idx ? dbg_face_idx : w.take<int64_t>((size_t)B * N);
+    float* bary = dbg_bary ? dbg_bary : w.take<float>((size_t)B * N * 3);
+    int64_t* npoints = dbg_npoints ? dbg_npoints : w.take<int64_t>((size_t)B * N * 2);
+    int64_t* rbound = dbg_rbound ? dbg_rbound : w.take<int64_t>((size_t)B);
+    float* noise = dbg_noise ? dbg_noise : w.take<float>((size_t)npx * 3);
+    float* centres = dbg_centres ? dbg_centres : w.take<float>((size_t)npx);
+    float* rmask = w.take<float>((size_t)npx);
+    SMK_REQUIRE(rmask != nullptr, "smk_masking_forward: workspace carve-up failed");
+    if (int rc = smk_masking_face_weights(h, trans_verts, base_prob, B, weights, ws, base, stream)) return rc;
+    {
+        static unsigned long long configured_mask = 0;
+        int dev = 0;
+        SMK_CHECK_CUDA(cudaGetDevice(&dev));
+        if (dev >= 64 || !(configured_mask & (1ull << dev))) {
+            SMK_CHECK_CUDA(cudaFuncSetAttribute(mask_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            if (dev < 64) configured_mask |= 1ull << dev;
+        }
+    }
+    SMK_TAG("mask_sample", 4.0 * B * d.F + 36.0 * B * N, 0.0, st);
+    SMK_LAUNCH(mask_sample_kernel, dim3(B), dim3(512), (size_t)d.F * sizeof(float), st, (const float*)weights, d.F, N, ratio_mul,
+               (const uint64_t*)rng_state, fidx, bary, rbound);
+    SMK_CHECK_LAUNCH();
+    if (int rc = smk_masking_points(h, trans_verts, fidx, bary, B, N, S, npoints, stream)) return rc;
+    SMK_TAG("mask_rng_fill", 16.0 * npx, 0.0, st);
+    SMK_LAUNCH(mask_rng_fill_kernel, dim3(smk::cdiv(npx, 256)), dim3(256), 0, st, B, S, p_centre, (const uint64_t*)rng_state, noise, centres);
+    SMK_CHECK_LAUNCH();
+    SMK_TAG("mask_rendered", 16.0 * npx, 0.0, st);
+    SMK_LAUNCH(mask_rendered_kernel, dim3(smk::cdiv(npx, 256)), dim3(256), 0, st, rendered, B, S, rmask);
+    SMK_CHECK_LAUNCH();
+    if (int rc = smk_masking_compose(h, img, hull, npoints, rbound, N, rmask, extra_noise ? noise : nullptr, p_centre > 0.f ? centres : nullptr,
+                                     wr, B, S, masked, ws, base, stream)) return rc;
+    SMK_TAG("mask_rng_advance", 16.0, 0.0, st);
+    SMK_LAUNCH(mask_rng_advance_kernel, dim3(1), dim3(32), 0, st, rng_state);
     SMK_CHECK_LAUNCH();
     return 0;
 }

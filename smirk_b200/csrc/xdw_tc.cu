@@ -45,7 +45,7 @@ constexpr int PAR_BYTES = 2 * PAR_ROWS * NC * 4;  // double-buffered: 3328 B
 constexpr int NUM_WORKERS = 256;
 constexpr int NUM_THREADS = 64 + NUM_WORKERS;
 constexpr int NUM_SPLITTERS = 128;              // 3xTF32 variant: four more warps split the landed x window into TF32 heads / tails
-constexpr uint32_t TMEM_COLS = 128;             // (2 buffers) x (2 halves) x 32 columns
+constexpr uint32_t TMEM_COLS = 128;             // (2 buffers) x (2 halves) x 32 columns; the 3xTF32 variant adds STAGES x 2 x 32 for the x tails
 
 using namespace ptx;                            // PTX wrappers shared by the tcgen05 kernels (tc_ptx.cuh)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) { return make_idesc_tf32(M, N); }
@@ -68,13 +68,20 @@ struct XdwArgs {
 // X3 = true: error-compensated 3xTF32 expand GEMM (fp32-equivalent e): x = x_hi + x_lo split in shared memory by four
 // dedicated warps (heads rewritten in place, tails in a second window), w1 = w_hi + w_lo split on the host (tmWlo);
 // e = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo accumulated in the same TMEM columns.  One CTA per SM (184 KB of shared memory).
-template <int STRIDE, bool X3>
+// X3 = 2: the tails of x live in TENSOR MEMORY (64 more columns per ring stage) instead of a second shared-memory window and
+// are multiplied with the A-from-TMEM form of tcgen05.mma — shared memory stays at the plain kernel's 113 KB + the weight
+// tails, so the SM keeps room for the other kernels of the concurrent pipeline.
+template <int STRIDE, int X3>
 __global__ void __launch_bounds__(NUM_THREADS + (X3 ? NUM_SPLITTERS : 0), X3 ? 1 : 2)
 xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
            const XdwArgs a) {
     constexpr int TO = STRIDE == 1 ? 14 : 7;                    // output tile edge
-    constexpr int STAGE_BYTES = (X3 ? 2 : 1) * smk::STAGE_BYTES;  // [x half 0][x half 1][w] (+ the same three again: tails)
-    constexpr int LO = smk::STAGE_BYTES;                        // offset of the tails within a stage
+    constexpr int STAGE_BYTES = X3 == 1 ? 2 * smk::STAGE_BYTES : (X3 == 2 ? smk::STAGE_BYTES + B_BYTES : smk::STAGE_BYTES);
+    constexpr int LO = smk::STAGE_BYTES;                        // X3 == 1: offset of the tails ([x half 0][x half 1][w] again) within a stage
+    constexpr int WLO = X3 == 1 ? LO + 2 * HALF_BYTES : smk::STAGE_BYTES;   // offset of the weight tails
+    constexpr uint32_t XLO_COL = smk::TMEM_COLS;                // X3 == 2: first TMEM column of the x tails (stage s, half h -> + (2 s + h) * 32)
+    constexpr uint32_t TMEM_COLS = X3 == 2 ? 256u : smk::TMEM_COLS;
+    static_assert(X3 != 2 || 128 + STAGES * 64 <= 256, "TMEM columns");
     constexpr uint32_t IDESC = make_idesc(128, NC);
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B; offset arithmetic (not an integer round-trip of the pointer) keeps
@@ -139,7 +146,7 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                         tma_load_4d(&tmX, st, &full[s], kb * BK, ex0, ey0, w.img);
                         tma_load_4d(&tmX, st + HALF_BYTES, &full[s], kb * BK, ex0, ey0 + 8, w.img);
                         tma_load_2d(&tmW, st + 2 * HALF_BYTES, &full[s], kb * BK, c * NC);
-                        if (X3) tma_load_2d(&tmWlo, st + LO + 2 * HALF_BYTES, &full[s], kb * BK, c * NC);
+                        if (X3) tma_load_2d(&tmWlo, st + WLO, &full[s], kb * BK, c * NC);
                     }
             }
         }
@@ -168,8 +175,9 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                             const uint64_t db = make_smem_desc(sb + k * UMMA_K * 4);
                             umma_tf32(d, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
                             if (X3) {
-                                umma_tf32(d, make_smem_desc(sa + LO + half * HALF_BYTES + k * UMMA_K * 4), db, IDESC, 1u);   // x_lo * w_hi
-                                umma_tf32(d, da, make_smem_desc(sb + LO + k * UMMA_K * 4), IDESC, 1u);                       // x_hi * w_lo
+                                if (X3 == 1) umma_tf32(d, make_smem_desc(sa + LO + half * HALF_BYTES + k * UMMA_K * 4), db, IDESC, 1u);   // x_lo * w_hi
+                                else umma_tf32_ts(d, tmem_base + XLO_COL + (uint32_t)((s * 2 + half) * 32 + k * UMMA_K), db, IDESC, 1u);
+                                umma_tf32(d, da, make_smem_desc(sa + WLO + k * UMMA_K * 4), IDESC, 1u);                      // x_hi * w_lo
                             }
                         }
                     tcgen05_commit(&empty[s]);
@@ -188,17 +196,38 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                 for (int kb = 0; kb < a.nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
-                    float4* X = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
-                    float4* XL = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + LO);
+                    if (X3 == 2) {
+                        // thread = window row t of each half (its TMEM lane): heads rewritten in place, tails -> tensor memory
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            uint8_t* row = smem + s * STAGE_BYTES + half * HALF_BYTES + t * 128;
+                            float lo[32];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float4* p = reinterpret_cast<float4*>(row + ((j ^ (t & 7)) << 4));
+                                const float4 v = *p;
+                                float4 hi;
+                                hi.x = round_tf32(v.x); hi.y = round_tf32(v.y); hi.z = round_tf32(v.z); hi.w = round_tf32(v.w);
+                                lo[4 * j] = v.x - hi.x; lo[4 * j + 1] = v.y - hi.y; lo[4 * j + 2] = v.z - hi.z; lo[4 * j + 3] = v.w - hi.w;
+                                *p = hi;
+                            }
+                            tmem_st32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + XLO_COL + (uint32_t)((s * 2 + half) * 32), lo);
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        tcgen05_fence_before();
+                    } else {
+                        float4* X = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+                        float4* XL = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + LO);
 #pragma unroll 4
-                    for (int j = 0; j < 2 * HALF_BYTES / 16 / NUM_SPLITTERS; ++j) {
-                        const float4 v = X[t + NUM_SPLITTERS * j];
-                        float4 hi, lo;
-                        hi.x = round_tf32(v.x); hi.y = round_tf32(v.y); hi.z = round_tf32(v.z); hi.w = round_tf32(v.w);
-                        lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;       // exact
-                        X[t + NUM_SPLITTERS * j] = hi; XL[t + NUM_SPLITTERS * j] = lo;
+                        for (int j = 0; j < 2 * HALF_BYTES / 16 / NUM_SPLITTERS; ++j) {
+                            const float4 v = X[t + NUM_SPLITTERS * j];
+                            float4 hi, lo;
+                            hi.x = round_tf32(v.x); hi.y = round_tf32(v.y); hi.z = round_tf32(v.z); hi.w = round_tf32(v.w);
+                            lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;       // exact
+                            X[t + NUM_SPLITTERS * j] = hi; XL[t + NUM_SPLITTERS * j] = lo;
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&split[s]);
                 }
@@ -418,17 +447,20 @@ int xdw_conv(const XdwConv& p, cudaStream_t st) {
     a.tiles_x = cdiv(Wo, TO); a.tiles_y = cdiv(Ho, TO);
     a.scale1 = p.scale1; a.bias1 = p.bias1; a.wdw = p.wdw; a.scale2 = p.scale2; a.bias2 = p.bias2; a.out = p.out; a.round_out = p.round_out;
     constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + E_BYTES + PAR_BYTES + 1024 + 256;
-    constexpr size_t smem3 = (size_t)STAGES * 2 * STAGE_BYTES + E_BYTES + PAR_BYTES + 1024 + 256;
+    constexpr size_t smem3 = (size_t)STAGES * 2 * STAGE_BYTES + E_BYTES + PAR_BYTES + 1024 + 256;          // tails in shared memory
+    constexpr size_t smem3t = (size_t)STAGES * (STAGE_BYTES + B_BYTES) + E_BYTES + PAR_BYTES + 1024 + 256;  // tails in tensor memory
     static_assert(2 * (smem + 1024) <= 228 * 1024, "two CTAs per SM");
     static_assert(smem3 + 1024 <= 227 * 1024, "3xTF32 variant: one CTA per SM");
     static unsigned long long configured_mask = 0;       // per-device attribute, see gemm_tc.cu
     int dev = 0;
     SMK_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !(configured_mask & (1ull << dev))) {
-        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3t));
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3t));
         if (dev < 64) configured_mask |= 1ull << dev;
     }
     {
@@ -439,12 +471,16 @@ int xdw_conv(const XdwConv& p, cudaStream_t st) {
     }
     a.n_items = a.tiles_x * a.tiles_y * p.B * a.groups;
     dim3 grid((unsigned)std::min(a.n_items, p.w1t_lo ? std::min(slots, 148) : slots));            // persistent: (up to) 2 CTAs per SM
-    if (p.w1t_lo) {
-        if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, true>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3, st, tmX, tmW, tmWlo, a);
-        else SMK_LAUNCH((xdw_kernel<2, true>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3, st, tmX, tmW, tmWlo, a);
+    static const int x3_tmem = []() { const char* e = getenv("SMK_X3_TMEM"); return e ? atoi(e) : 1; }();
+    if (p.w1t_lo && x3_tmem) {
+        if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, 2>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3t, st, tmX, tmW, tmWlo, a);
+        else SMK_LAUNCH((xdw_kernel<2, 2>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3t, st, tmX, tmW, tmWlo, a);
+    } else if (p.w1t_lo) {
+        if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, 1>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3, st, tmX, tmW, tmWlo, a);
+        else SMK_LAUNCH((xdw_kernel<2, 1>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3, st, tmX, tmW, tmWlo, a);
     } else {
-        if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, false>), dim3(grid), dim3(NUM_THREADS), smem, st, tmX, tmW, tmWlo, a);
-        else SMK_LAUNCH((xdw_kernel<2, false>), dim3(grid), dim3(NUM_THREADS), smem, st, tmX, tmW, tmWlo, a);
+        if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, 0>), dim3(grid), dim3(NUM_THREADS), smem, st, tmX, tmW, tmWlo, a);
+        else SMK_LAUNCH((xdw_kernel<2, 0>), dim3(grid), dim3(NUM_THREADS), smem, st, tmX, tmW, tmWlo, a);
     }
     SMK_CHECK_LAUNCH();
     return 0;

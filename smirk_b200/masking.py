@@ -1,5 +1,4 @@
-"""Masking between Renderer and SmirkGenerator on the GPU — WORK IN PROGRESS, not yet validated on
-a GPU (branch wip/masking-kernels).
+"""Masking between Renderer and SmirkGenerator on the GPU.
 
 Mirrors ``src/utils/masking.py``: ``mesh_based_mask_uniform_faces`` and ``masking`` keep the reference's names,
 arguments and return values.  Random draws (multinomial, rand, randn, bernoulli) are made with torch on the tensors'
@@ -24,16 +23,10 @@ class MaskingContext:
         self._faces_host = f
         self.n_verts, self.n_faces = int(n_verts), int(f.shape[0])
         L = _lib.lib()
-        self._h = C.c_void_p()
+        h = C.c_void_p()
         desc = SmkMaskingDesc(self.n_verts, self.n_faces, f.data_ptr())
-        _lib.check(L.smk_masking_create(C.byref(desc), C.byref(self._h)), "smk_masking_create")
-
-    def __del__(self):
-        try:
-            if getattr(self, "_h", None):
-                _lib.lib().smk_masking_destroy(self._h)
-        except Exception:
-            pass
+        _lib.check(L.smk_masking_create(C.byref(desc), C.byref(h)), "smk_masking_create")
+        self._h = _lib.NativeHandle(h, "smk_masking_destroy")
 
     def workspace(self, B, S, device):
         n = int(_lib.lib().smk_masking_workspace_bytes(self._h, B, S))
@@ -109,7 +102,7 @@ def masking_from_points(img, mask, npoints, rbound, wr=15, rendered_mask=None, n
         return out
     P = lambda t: 0 if t is None else t.to(img.device, torch.float32).contiguous().data_ptr()
     keep = [t.to(img.device, torch.float32).contiguous() if t is not None else None for t in (mask, rendered_mask, noise_mult, random_centres)]
-    npts = npoints.to(img.device, torch.int64).contiguous()
+    npts = npoints[..., :2].to(img.device, torch.int64).contiguous()      # the reference's npoints may carry a third (z) column
     rb = rbound.to(img.device, torch.int64).contiguous()
     ws, n = ctx.workspace(B, S, img.device)
     ptr = lambda t: 0 if t is None else t.data_ptr()
@@ -117,3 +110,78 @@ def masking_from_points(img, mask, npoints, rbound, wr=15, rendered_mask=None, n
                                               ptr(keep[1]), ptr(keep[2]), ptr(keep[3]), int(wr), B, S, out.data_ptr(),
                                               ws.data_ptr(), n, _lib.stream_ptr(img.device)), "smk_masking_compose")
     return out
+
+
+class MaskingStage:
+    """The masking step of the full cycle (``demo.py:138-165``) as one capturable device call:
+    ``rendered_img, transformed_vertices, img, hull_mask -> masked_img`` with every random draw made on the device by a
+    counter-based generator (``csrc/masking.cu``, Philox4x32-10).  ``rng_state`` = (seed, call counter) lives in device
+    memory; each call advances the counter on the stream, so a CUDA-graph replay draws fresh samples.
+
+    Parameters follow the script: ``mask_ratio = 0.01``, ``mask_ratio_mul = 5`` (upper bound on the sampled points),
+    ``mask_dilation_radius = 10``; ``extra_noise`` / ``random_mask`` are ``masking()``'s defaults (masking.py:71)."""
+
+    def __init__(self, flame_faces, face_probabilities, n_verts=5023, mask_ratio=0.01, mask_ratio_mul=5, mask_dilation_radius=10,
+                 extra_noise=True, random_mask=0.01, image_size=224, seed=0):
+        self.faces = flame_faces.detach().to("cpu", torch.int64)
+        self.n_verts, self.S = int(n_verts), int(image_size)
+        self.base_prob_host = face_probabilities.detach().to("cpu", torch.float32).contiguous()
+        self.ratio_mul, self.wr = float(mask_ratio_mul), int(mask_dilation_radius)
+        self.N = int(mask_ratio * mask_ratio_mul * image_size * image_size)
+        self.extra_noise, self.p_centre, self.seed = bool(extra_noise), float(random_mask), int(seed)
+        self._ctx, self._dev, self._ws = None, {}, _lib.Workspace()
+
+    def __deepcopy__(self, memo):
+        new = MaskingStage.__new__(MaskingStage)
+        new.__dict__.update(self.__dict__)
+        new._ctx, new._dev, new._ws = None, {}, _lib.Workspace()
+        return new
+
+    @property
+    def _handle(self):                          # for SmirkPipeline's keep-alive list
+        return self._ctx
+
+    def _state(self, device):
+        if self._ctx is None:
+            with torch.cuda.device(device):
+                self._ctx = MaskingContext(self.faces, self.n_verts)
+        if device not in self._dev:
+            rng = torch.tensor([self.seed, 0], dtype=torch.int64, device=device)
+            self._dev[device] = (self.base_prob_host.to(device), rng)
+        return self._dev[device]
+
+    def reseed(self, seed, counter=0):
+        self.seed = int(seed)
+        for _, rng in self._dev.values():
+            rng.copy_(torch.tensor([self.seed, int(counter)], dtype=torch.int64))
+
+    @torch.no_grad()
+    def forward(self, img, hull_mask, transformed_vertices, rendered_img, debug=False):
+        _lib.require_cuda(img, "img")
+        dev = img.device
+        img, hull = _lib.dev_f32(img, "img"), _lib.dev_f32(hull_mask, "hull_mask")
+        tv, rend = _lib.dev_f32(transformed_vertices, "transformed_vertices"), _lib.dev_f32(rendered_img, "rendered_img")
+        B, S, N = img.shape[0], self.S, self.N
+        if tuple(img.shape[1:]) != (3, S, S) or tuple(rend.shape) != tuple(img.shape) or hull.numel() != B * S * S or tuple(tv.shape) != (B, self.n_verts, 3):
+            raise RuntimeError("smirk_b200.MaskingStage: expected img/rendered [B,3,%d,%d], hull [B,1,%d,%d], transformed_vertices [B,%d,3]" % (S, S, S, S, self.n_verts))
+        base_prob, rng = self._state(dev)
+        out = torch.empty_like(img)
+        dbg = {}
+        if debug:
+            i64 = lambda *s: torch.empty(*s, dtype=torch.int64, device=dev)
+            f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+            dbg = dict(sampled_faces_indices=i64(B, N), barycentric_coords=f32(B, N, 3), npoints=i64(B, N, 2), rbound=i64(B),
+                       noise_mult=f32(B, 3, S, S), random_centres=f32(B, 1, S, S))
+        L = _lib.lib()
+        P = lambda k: _lib.ptr(dbg.get(k))
+        with torch.cuda.device(dev):
+            n = int(L.smk_masking_forward_workspace_bytes(self._ctx._h, B, S, N))
+            ws = self._ws.get(n, dev)
+            _lib.check(L.smk_masking_forward(self._ctx._h, _lib.ptr(img), _lib.ptr(hull), _lib.ptr(tv), _lib.ptr(rend), _lib.ptr(base_prob),
+                                             B, S, N, self.wr, self.ratio_mul, self.p_centre, 1 if self.extra_noise else 0, _lib.ptr(rng),
+                                             _lib.ptr(out), P("sampled_faces_indices"), P("barycentric_coords"), P("npoints"), P("rbound"),
+                                             P("noise_mult"), P("random_centres"), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+                       "smk_masking_forward")
+        return (out, dbg) if debug else out
+
+    __call__ = forward

@@ -61,7 +61,7 @@ class _Lane:
     """One pipeline lane: a set of modules, a compute stream, a copy stream, per-batch-size graphs."""
 
     def __init__(self, modules, device, own_stream):
-        self.encoder, self.flame, self.renderer, self.generator = modules
+        self.encoder, self.flame, self.renderer, self.generator, self.masking = modules
         self.stream = torch.cuda.Stream(device=device) if own_stream else None
         self.graphs = {}
         self.host = {}
@@ -73,17 +73,20 @@ class _Lane:
         self.gather_out = {}
 
     def modules(self):
-        return [m for m in (self.encoder, self.flame, self.renderer, self.generator) if m is not None]
+        return [m for m in (self.encoder, self.flame, self.renderer, self.generator, self.masking) if m is not None]
 
 
 class SmirkPipeline:
     OUT_KEYS = ("rendered_img", "vertices", "transformed_vertices", "landmarks_fan", "landmarks_mp", "params")
 
-    def __init__(self, encoder, flame, renderer, generator=None, device="cuda:0", slots=2):
+    def __init__(self, encoder, flame, renderer, generator=None, device="cuda:0", slots=2, masking=None):
+        """``masking``: a ``smirk_b200.masking.MaskingStage``.  With it the full cycle computes the generator's second
+        input itself (demo.py:138-165) and the auxiliary input of forward/replay/submit/run_host is the landmark hull mask
+        [B,1,224,224]; without it the auxiliary input is a ready-made ``masked_img`` [B,3,224,224]."""
         self.device = torch.device(device)
-        self.encoder, self.flame, self.renderer, self.generator = encoder, flame, renderer, generator
+        self.encoder, self.flame, self.renderer, self.generator, self.masking = encoder, flame, renderer, generator, masking
         self.slots = max(1, int(slots))
-        self._lanes = [_Lane((encoder, flame, renderer, generator), self.device, own_stream=False)]
+        self._lanes = [_Lane((encoder, flame, renderer, generator, masking), self.device, own_stream=False)]
         self._h2d = self._d2h = None
         self._gather_keys, self._gather_group, self._comm = (), None, None
 
@@ -91,14 +94,14 @@ class SmirkPipeline:
         """Drop every captured graph (and the weights / workspaces they kept alive) and the lane replicas, so the next
         call re-captures from the current state of the caller's modules."""
         torch.cuda.synchronize(self.device)
-        self._lanes = [_Lane((self.encoder, self.flame, self.renderer, self.generator), self.device, own_stream=False)]
+        self._lanes = [_Lane((self.encoder, self.flame, self.renderer, self.generator, self.masking), self.device, own_stream=False)]
 
     def _lane(self, i):
         """Lane 0 runs the caller's modules on the caller's stream; lanes >= 1 are replicas (deep copies:
         same parameter values, separate native handles / workspaces) on their own streams."""
         while len(self._lanes) <= i:
             mods = tuple(copy.deepcopy(m) if m is not None else None
-                         for m in (self.encoder, self.flame, self.renderer, self.generator))
+                         for m in (self.encoder, self.flame, self.renderer, self.generator, self.masking))
             self._lanes.append(_Lane(mods, self.device, own_stream=True))
         return self._lanes[i]
 
@@ -119,7 +122,11 @@ class SmirkPipeline:
         }
         if L.generator is not None:
             if masked_img is None:
-                raise RuntimeError("SmirkPipeline: the generator stage needs `masked_img` (demo.py:165-167)")
+                raise RuntimeError("SmirkPipeline: the generator stage needs `masked_img` (demo.py:165-167), or the hull mask "
+                                   "when a MaskingStage is attached")
+            if L.masking is not None:           # the auxiliary input is the hull mask: demo.py:138-165 on the device
+                masked_img = L.masking(img, masked_img, ro["transformed_vertices"], ro["rendered_img"])
+                out["masked_img"] = masked_img
             out["reconstructed_img"] = L.generator(torch.cat([ro["rendered_img"], masked_img], 1))
         return out
 
@@ -131,7 +138,7 @@ class SmirkPipeline:
             return L.graphs[B]
         dev = self.device
         static_in = torch.zeros(B, 3, 224, 224, device=dev)
-        static_mask = torch.zeros(B, 3, 224, 224, device=dev) if self.generator is not None else None
+        static_mask = torch.zeros(B, 1 if self.masking is not None else 3, 224, 224, device=dev) if self.generator is not None else None
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                       # warm-up: builds handles, sizes workspaces
@@ -307,7 +314,7 @@ class SmirkPipeline:
 
     def bytes_per_step(self, B, keys=("rendered_img", "vertices", "params")):
         rec = self.capture(B)
-        h2d = B * 3 * 224 * 224 * 4 * (2 if rec["mask"] is not None else 1)
+        h2d = B * 3 * 224 * 224 * 4 + (rec["mask"].numel() * 4 if rec["mask"] is not None else 0)
         d2h = sum(rec["out"][k].numel() * rec["out"][k].element_size() for k in keys)
         return h2d, d2h
 
