@@ -104,7 +104,7 @@ class ClockSampler:
 
 def workload_name(generator, batch):
     if generator:
-        return "configs[2]: full cycle encoder->FLAME->raster->smirk_generator 224x224, batch %d per GPU" % batch
+        return "configs[2]: full cycle encoder->FLAME->raster->masking->smirk_generator 224x224, batch %d per GPU" % batch
     return "configs[1]: encoder+FLAME+raster 224x224, batch %d per GPU" % batch
 
 
@@ -130,7 +130,10 @@ def cpu_reference_pass(root, sample, with_generator, threads=None, seed=9001):
         gen = smirk_b200.SmirkGenerator(6, 3, 32, 5)
         st["gen_sd"] = synth_inputs.random_state_dict(gen.state_dict(), seed=7)
     img = synth_inputs.images(sample, seed)
-    mask = synth_inputs.masked_images(sample, seed + 1) if with_generator else None
+    hull = synth_inputs.hull_masks(sample, seed + 1) if with_generator else None
+    if with_generator:
+        from oracle import masking_ref
+        base_prob = synth_inputs.face_probabilities(st["fc"].faces_tensor.shape[0])
     t0 = time.perf_counter()
     with torch.no_grad():
         p = encoder_ref.encoder_forward_ref(st["enc_sd"], img)
@@ -138,8 +141,21 @@ def cpu_reference_pass(root, sample, with_generator, threads=None, seed=9001):
         fo = flame_ref.flame_forward_ref(st["fc"], p)
         ro = render_ref.render_forward_ref(st["rc"], fo["vertices"], p["cam"], landmarks_fan=fo["landmarks_fan"],
                                            landmarks_mp=fo["landmarks_mp"])
-        if with_generator:
-            generator_ref.generator_forward_ref(st["gen_sd"], torch.cat([ro["rendered_img"], mask], 1))
+        if with_generator:                                                     # demo.py:138-167 on the CPU (torch RNG draws)
+            tv, faces, N = ro["transformed_vertices"], st["fc"].faces_tensor, int(0.05 * 224 * 224)
+            w = masking_ref.face_probabilities_ref(tv, faces, base_prob)
+            idx = torch.multinomial(w, N, replacement=True)
+            u, v = torch.rand(sample * N), torch.rand(sample * N)
+            o = u + v > 1
+            u[o], v[o] = 1 - u[o], 1 - v[o]
+            pts = masking_ref.points_from_coords_ref(tv, faces, idx, torch.stack((1 - (u + v), u, v), 1).view(sample, N, 3))
+            rsing = torch.randint(0, 2, (sample,)) * 2 - 1
+            rbound = (N * 0.2 * (torch.rand(sample) * 4 + 1) ** rsing).long()
+            rmask = 1 - (ro["rendered_img"] == 0).all(dim=1, keepdim=True).float()
+            masked = masking_ref.masking_ref(img, hull, img * masking_ref.point_mask_ref(pts, rbound, 224), 10, rendered_mask=rmask,
+                                             noise_mult=torch.randn(img.shape) * 0.05 + 1,
+                                             random_centres=torch.bernoulli(torch.ones(sample, 1, 224, 224) * 0.01))
+            generator_ref.generator_forward_ref(st["gen_sd"], torch.cat([ro["rendered_img"], masked], 1))
     return time.perf_counter() - t0
 
 
@@ -280,13 +296,17 @@ def run_workload(cx, args, B, generator, slots, R, with_cpu):
         gen = gen.eval().to(dev)
         gen.precision = 0 if args.precision == "fp32" else 1
     fl, rd = smirk_b200.FLAME().to(dev), smirk_b200.Renderer().to(dev)
-    pipe = SmirkPipeline(enc, fl, rd, gen, device=dev, slots=slots)
+    stage = None
+    if generator:                               # the real masking step between renderer and generator (demo.py:138-165), draws on the device
+        from smirk_b200.masking import MaskingStage
+        stage = MaskingStage(fl.faces_tensor, synth_inputs.face_probabilities(fl.faces_tensor.shape[0]), seed=1234 + rank)
+    pipe = SmirkPipeline(enc, fl, rd, gen, device=dev, slots=slots, masking=stage)
 
     # rotating input set larger than L2 (126 MB): Rset batches of B x 602 KB (x2 with the masked image)
-    per = B * 3 * 224 * 224 * 4 * (2 if generator else 1)
+    per = B * 224 * 224 * 4 * (4 if generator else 3)
     Rset = max(2, -(-160_000_000 // per))
     host_imgs = [synth_inputs.images(B, 5000 + rank * 100 + i).pin_memory() for i in range(Rset)]
-    host_masks = [synth_inputs.masked_images(B, 6000 + rank * 100 + i).pin_memory() for i in range(Rset)] if generator else None
+    host_masks = [synth_inputs.hull_masks(B, 6000 + rank * 100 + i).pin_memory() for i in range(Rset)] if generator else None
     dev_imgs = [h.to(dev) for h in host_imgs]
     dev_masks = [h.to(dev) for h in host_masks] if generator else None
     rec = pipe.capture(B)

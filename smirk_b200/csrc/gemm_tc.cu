@@ -50,8 +50,10 @@ struct TcArgs {
     const float* res; int ld_res; int res_pad;   // residual (optionally read from the interior of a padded buffer)
     int relu;
     float* out; int ld_out;
-    int store;                     // 0 plain, 1 pixel-shuffle (N = 4*Cout), 2 interior of a (H+2)x(W+2) padded buffer
+    int store;                     // 0 plain, 1 pixel-shuffle (N = 4*Cout), 2 interior of a (H+2)x(W+2) padded buffer,
+                                   // 3 fused head: out[b, co, h, w] = sigmoid(head_b[co] + sum_n act[m, n] * head_w[n][co]) (NCHW, N <= 32)
     int round_out;                 // 1: round the stored activations to TF32 (round-to-nearest) for the next tensor-core layer
+    const float* head_w; const float* head_b; int head_c;      // store 3: 1x1 head weights [N][head_c], bias [head_c], head_c <= 4
 };
 
 template <int BN, int STAGES, int MINB, bool PERSIST, int X3>
@@ -293,6 +295,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
                         }
                         if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        if (a.store == 3) {
+                            // fused 1x1 head + sigmoid (smirk_generator.py:77-78 -> :86): the 8 lanes of a row hold its N <= 32
+                            // activations, 4 each; partial dot products, butterfly over the 8 lanes, lane 0 of the row stores
+                            // NCHW.  The activation tensor itself is never written.
+                            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                            const float xs[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                                for (int co = 0; co < 4; ++co)
+                                    if (co < a.head_c) acc[co] = fmaf(xs[q], __ldg(a.head_w + (size_t)(nc + q) * a.head_c + co), acc[co]);
+#pragma unroll
+                            for (int co = 0; co < 4; ++co) {
+                                acc[co] += __shfl_xor_sync(__activemask(), acc[co], 1);
+                                acc[co] += __shfl_xor_sync(__activemask(), acc[co], 2);
+                                acc[co] += __shfl_xor_sync(__activemask(), acc[co], 4);
+                            }
+                            if (jj == 0) {
+                                const int hw = a.H * a.W, b = opix[i] / hw, rem = opix[i] - b * hw;
+                                for (int co = 0; co < a.head_c; ++co)
+                                    a.out[((size_t)b * a.head_c + co) * hw + rem] = 1.f / (1.f + __expf(-(acc[co] + __ldg(a.head_b + co))));
+                            }
+                            continue;
+                        }
                         if (a.round_out) { o.x = smk::round_tf32(o.x); o.y = smk::round_tf32(o.y); o.z = smk::round_tf32(o.z); o.w = smk::round_tf32(o.w); }
                         *reinterpret_cast<float4*>(a.out + (size_t)(opix[i] + pix_off) * a.ld_out + col) = o;
                     }
@@ -418,6 +444,13 @@ int tc_conv(const TcConv& p, cudaStream_t st) {
     SMK_REQUIRE(p.mode == 0 || (p.Cin % BK == 0 && p.K == 9 * p.Cin), "tc_conv: 3x3 mode needs Cin %% 32 == 0 (got %d)", p.Cin);
     SMK_REQUIRE(p.store != 1 || ((p.N / 4) % 32 == 0), "tc_conv: pixel-shuffle store needs Cout %% 32 == 0");
     int BN = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
+    // Wide layers (N >= 256: the generator's 28^2 / 14^2 convolutions, 75 % of its FLOPs): a 128 x 256 tile halves the
+    // A-operand bytes the tensor core pulls from shared memory per FLOP.  TF32 operands are 4 bytes, so at BN = 128 the
+    // MMA reads (A 4 KB + B 4 KB per 64-cycle instruction) plus the TMA fill already ask for ~2x the 128 B/clk an SM's
+    // shared memory delivers; at BN = 256 the demand drops to ~1.5x.  One persistent CTA per SM, 4-stage ring (192 KB),
+    // both accumulators (2 x 256 columns) fill the SM's tensor memory.  SMK_TC_BN256=0 restores 128-wide tiles.
+    static const int bn256 = []() { const char* e = getenv("SMK_TC_BN256"); return e ? atoi(e) : 1; }();
+    if (bn256 && p.mode != 0 && p.N % 256 == 0 && !p.wt_lo) BN = 256;
     // Few-tile, deep-K problems (the encoder's 7x7 / 14x14 projections: M = 1568..6272, K up to 960) are a serial
     // chain of k-blocks on a handful of SMs: narrower N tiles put more CTAs to work.  An 8-stage ring with one
     // CTA per SM (SMK_TC_DEEP_SMALL=1) makes such a kernel ~20 % faster when it runs ALONE, but its 177 KB of
@@ -439,6 +472,9 @@ int tc_conv(const TcConv& p, cudaStream_t st) {
     a.cpb = p.mode == 0 ? 1 : p.Cin / BK; a.lc = p.mode == 2 ? 0 : -1;
     a.scale = p.scale; a.bias = p.bias; a.res = p.res; a.ld_res = p.ld_res; a.res_pad = p.res_pad; a.relu = p.relu;
     a.out = p.out; a.ld_out = p.ld_out; a.store = p.store; a.round_out = p.round_out;
+    a.head_w = p.head_w; a.head_b = p.head_b; a.head_c = p.head_c;
+    SMK_REQUIRE(p.store != 3 || (p.N <= 32 && p.head_w && p.head_b && p.head_c >= 1 && p.head_c <= 4 && !p.res),
+                "tc_conv: the fused 1x1 head needs N <= 32 (one column tile) and 1..4 head channels");
     if (p.mode == 0) {
         if (int rc = encode_2d(&tmA, p.in, (uint64_t)M, (uint64_t)p.K, (uint64_t)p.ld_in, BM)) return rc;
     } else if (p.mode == 1) {
@@ -477,6 +513,7 @@ int tc_conv(const TcConv& p, cudaStream_t st) {
     // 3x3 convolutions (deep K): persistent CTAs for the narrow-N layers and for the few-tile 14x14 layers;
     // the wide-N layers are bound by the shared-memory fill rate either way and keep two single-tile CTAs per SM.
     const bool persist = persist_mode >= 0 ? persist_mode != 0 : (p.mode != 0 && (BN <= 64 || n_tiles <= 2 * 148));
+    if (BN == 256) return launch<256, 4, 1, true>(tmA, tmB, a, st);
     if (persist) {
         if (BN == 32) return launch<32, 4, 2, true>(tmA, tmB, a, st);
         if (BN == 64) return launch<64, 3, 2, true>(tmA, tmB, a, st);

@@ -15,7 +15,9 @@ struct TcConv {
     int relu;
     const float* res; int ld_res; int res_pad;   // residual; res_pad: read it from the interior of a padded buffer
     float* out; int ld_out;
-    int store;                           // 0 plain, 1 pixel-shuffle (N = 4*Cout), 2 interior of a (H+2)x(W+2) padded buffer
+    int store;                           // 0 plain, 1 pixel-shuffle (N = 4*Cout), 2 interior of a (H+2)x(W+2) padded buffer,
+                                         // 3 fused 1x1 head + sigmoid: out is [B, head_c, H, W] NCHW, the activations are not stored
+    const float* head_w; const float* head_b; int head_c;     // store 3: head weights [N][head_c], bias [head_c]
     int round_out;                       // 1: round stored activations to TF32 (RN) — they feed another tensor-core layer
 };
 

@@ -8,8 +8,10 @@
 //
 // precision 0: every convolution runs on the fp32 CUDA-core implicit GEMM (nn_kernels.cu); reflection
 //              padding (:147-171) is resolved in the A-operand loader.
-// precision 1: every convolution with Cin % 32 == 0 (all but the very first, Cin = 6) runs on the TF32
-//              tcgen05 implicit GEMM (gemm_tc.cu).  The ResNet blocks keep their activations in
+// precision 1: every convolution runs on the TF32 tcgen05 implicit GEMM (gemm_tc.cu); the very first one (Cin = 6)
+//              reads an input whose channels are zero-padded to 32 by the layout-conversion kernel (one 128-byte
+//              SWIZZLE_128B row per pixel: the im2col TMA path as is; 2.3x faster than the fp32 CUDA-core kernel it
+//              replaces even though 26 of the 32 K-columns per tap multiply zeros).  The ResNet blocks keep their activations in
 //              reflection-padded [B,16,16,512] buffers: each conv's epilogue writes the interior, a
 //              tiny kernel mirrors the 1-pixel halo, and the next conv's im2col TMA reads it with no
 //              padding — the hardware cannot reflect, so the halo is made explicit once per layer.
@@ -97,7 +99,8 @@ extern "C" int smk_generator_create(const SmkGeneratorDesc* desc, SmkGenerator**
     SMK_REQUIRE(desc->precision == 0 || desc->init_features % 32 == 0, "smk_generator_create: the tcgen05 path needs init_features %% 32 == 0");
     if (desc->precision == 1) { if (int rc = smk::tc_init()) return rc; }
     SmkGenerator* h = new SmkGenerator();
-    h->cin = desc->in_channels; h->cin_p = (desc->in_channels + 7) & ~7; h->cout = desc->out_channels;
+    h->cin = desc->in_channels; h->cout = desc->out_channels;
+    h->cin_p = desc->precision == 1 ? (desc->in_channels + 31) & ~31 : (desc->in_channels + 7) & ~7;
     h->f = desc->init_features; h->nres = desc->res_blocks; h->precision = desc->precision;
     const int f = h->f;
     const bool tc = h->precision == 1;
@@ -107,7 +110,7 @@ extern "C" int smk_generator_create(const SmkGeneratorDesc* desc, SmkGenerator**
     int c_in = h->cin, c_in_p = h->cin_p;
     for (int l = 0; ok && l < 5; ++l) {
         int co = f << l;
-        ok = fold_conv3(cur, c_in, c_in_p, co, tc && l > 0, h->arena, &h->enc[l][0], &e) &&
+        ok = fold_conv3(cur, c_in, c_in_p, co, tc, h->arena, &h->enc[l][0], &e) &&
              fold_conv3(cur, co, co, co, tc, h->arena, &h->enc[l][1], &e);
         c_in = c_in_p = co;
     }
@@ -168,9 +171,10 @@ Plan make_plan(const SmkGenerator* h) {
 //   refl   : reflection padding (ResNet blocks).  At precision 1 `in` must then be a padded buffer.
 //   store  : 0 plain / slice, 2 interior of a padded buffer (precision 1 only)
 int conv3(const SmkGenerator* h, const Conv3& c, const float* in, int ld_in, int B, int S, bool refl, bool relu,
-          const float* res, int res_pad, float* out, int ld_out, int store, cudaStream_t st) {
+          const float* res, int res_pad, float* out, int ld_out, int store, cudaStream_t st, bool fuse_head = false) {
     if (c.wt) {
         TcConv p{};
+        if (fuse_head) { p.head_w = h->fw; p.head_b = h->fb; p.head_c = h->cout; }
         p.in = in; p.ld_in = ld_in; p.B = B; p.H = S; p.W = S; p.Cin = c.cin_p; p.wt = c.wt; p.scale = c.scale; p.bias = c.bias;
         p.N = c.cout; p.K = 9 * c.cin_p; p.mode = refl ? 2 : 1; p.relu = relu ? 1 : 0;
         p.res = res; p.ld_res = c.cout; p.res_pad = res_pad; p.out = out; p.ld_out = ld_out; p.store = store; p.round_out = 1;
@@ -209,7 +213,7 @@ extern "C" int smk_generator_forward(const SmkGenerator* h, const float* x, int 
     float* pad[3] = {nullptr, nullptr, nullptr};
     if (tc) for (int i = 0; i < 3; ++i) pad[i] = w.take<float>(P.pad[i] * B);
     SMK_REQUIRE(b1 != nullptr && (!tc || pad[2] != nullptr), "smk_generator_forward: workspace carve-up failed");
-    int rc = smk::nchw_to_nhwc_pad(x, B, h->cin, 224, 224, h->cin_p, x8, st);
+    int rc = smk::nchw_to_nhwc_pad(x, B, h->cin, 224, 224, h->cin_p, x8, st, tc);
     if (rc) return rc;
     // encoder levels: conv1 -> t[l]; conv2 -> upper half of cat[l] (the skip); pool -> p[l]
     const float* in = x8; int ld = h->cin_p;
@@ -265,6 +269,11 @@ extern "C" int smk_generator_forward(const SmkGenerator* h, const float* x, int 
         }
         dS *= 2;
         if ((rc = conv3(h, h->dec[l][0], cat[lvl], 2 * u.cout, B, dS, false, true, nullptr, 0, t[lvl], u.cout, 0, st))) return rc;
+        // last layer of the tensor-core path: the 1x1 conv + sigmoid (smirk_generator.py:77-78,86) rides in the epilogue of
+        // dec1conv2 — the [B,224,224,32] activation (6.4 MB per face) is neither written nor read back
+        static const int fuse_head_env = []() { const char* e = getenv("SMK_FUSE_HEAD"); return e ? atoi(e) : 1; }();
+        const bool fuse_head = l == 3 && tc && fuse_head_env && u.cout <= 32;
+        if (fuse_head) return conv3(h, h->dec[l][1], t[lvl], u.cout, B, dS, false, true, nullptr, 0, y, u.cout, 3, st, true);
         if ((rc = conv3(h, h->dec[l][1], t[lvl], u.cout, B, dS, false, true, nullptr, 0, d[lvl], u.cout, 0, st))) return rc;
         din = d[lvl];
     }

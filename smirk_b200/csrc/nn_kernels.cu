@@ -389,13 +389,22 @@ maxpool2x2_kernel(const float* __restrict__ in, int ld_in, int B, int H, int W, 
 }
 
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_pad_kernel(const float* __restrict__ in, int B, int C, int HW, int Cp, float* __restrict__ out) {
+nchw_to_nhwc_pad_kernel(const float* __restrict__ in, int B, int C, int HW, int Cp, int round, float* __restrict__ out) {
+    // thread = (pixel, channel quad), quads of a pixel in adjacent lanes: every warp stores 512 contiguous bytes
     pdl_sync();
-    long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= (long)B * HW) return;
-    int b = (int)(pix / HW); int r = (int)(pix - (long)b * HW);
-    for (int c = 0; c < Cp; ++c)
-        out[(size_t)pix * Cp + c] = c < C ? in[((size_t)b * C + c) * HW + r] : 0.f;
+    const int Q = Cp >> 2;
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)B * HW * Q) return;
+    const int q = (int)(i % Q); const long pix = i / Q;
+    const int b = (int)(pix / HW); const int r = (int)(pix - (long)b * HW);
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = q * 4 + k;
+        v[k] = c < C ? __ldg(in + ((size_t)b * C + c) * HW + r) : 0.f;
+        if (round) v[k] = round_tf32(v[k]);
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -675,9 +684,10 @@ int maxpool2x2(const float* in, int ld_in, int B, int H, int W, int C, float* ou
     return 0;
 }
 
-int nchw_to_nhwc_pad(const float* in, int B, int C, int H, int W, int Cp, float* out, cudaStream_t st) {
+int nchw_to_nhwc_pad(const float* in, int B, int C, int H, int W, int Cp, float* out, cudaStream_t st, bool round_out) {
+    SMK_REQUIRE(Cp % 4 == 0 && Cp >= C, "nchw_to_nhwc_pad: padded channel count must be a multiple of 4 and >= C");
     SMK_TAG("nchw_to_nhwc", 4.0 * (double)B * H * W * (C + Cp), 0.0, st);
-    SMK_LAUNCH(nchw_to_nhwc_pad_kernel, dim3(cdiv((long)B * H * W, 256)), dim3(256), 0, st, in, B, C, H * W, Cp, out);
+    SMK_LAUNCH(nchw_to_nhwc_pad_kernel, dim3(cdiv((long)B * H * W * (Cp / 4), 256)), dim3(256), 0, st, in, B, C, H * W, Cp, round_out ? 1 : 0, out);
     SMK_CHECK_LAUNCH();
     return 0;
 }

@@ -44,7 +44,8 @@ int stem_ds(const float* img_nchw, int B, int H, int W, const float* stem_w /*[2
             const float* dw_w /*[9][16]*/, const float* dw_s, const float* dw_b, const float* pw_w /*[16][16]*/, const float* pw_s,
             const float* pw_b, int stride, int round_out, float* out, cudaStream_t st);
 int maxpool2x2(const float* in, int ld_in, int B, int H, int W, int C, float* out, cudaStream_t st);
-int nchw_to_nhwc_pad(const float* in, int B, int C, int H, int W, int Cp, float* out, cudaStream_t st);
+// NCHW -> NHWC with the channel count zero-padded to Cp (a multiple of 4); round_out rounds to TF32 for a tensor-core consumer.
+int nchw_to_nhwc_pad(const float* in, int B, int C, int H, int W, int Cp, float* out, cudaStream_t st, bool round_out = false);
 // out[b, co, h, w] = sigmoid(bias[co] + sum_c in[b,h,w,c] * w[c][co])   (NHWC -> NCHW)
 int conv1x1_sigmoid_nchw(const float* in, int B, int HW, int Cin, const float* w /*[Cin][Cout]*/, const float* bias,
                          int Cout, float* out, cudaStream_t st);

@@ -37,6 +37,24 @@ def masked_images(B, seed):
     return torch.rand(B, 3, 224, 224, generator=g) * m
 
 
+def hull_masks(B, seed):
+    """Stand-in for ``create_mask(landmarks)`` (datasets/base_dataset.py:9-15, demo.py:142): [B,1,224,224], 0 inside a
+    face-sized ellipse (the landmark hull), 1 outside."""
+    g = torch.Generator().manual_seed(seed)
+    cx, cy = 112 + (torch.rand(B, generator=g) - 0.5) * 16, 116 + (torch.rand(B, generator=g) - 0.5) * 16
+    ax, ay = 58 + torch.rand(B, generator=g) * 14, 76 + torch.rand(B, generator=g) * 14
+    y, x = torch.meshgrid(torch.arange(224.0), torch.arange(224.0), indexing="ij")
+    inside = ((x[None] - cx[:, None, None]) / ax[:, None, None]) ** 2 + ((y[None] - cy[:, None, None]) / ay[:, None, None]) ** 2 < 1
+    return (~inside).float()[:, None].contiguous()
+
+
+def face_probabilities(n_faces, seed=11):
+    """Stand-in for ``load_probabilities_per_FLAME_triangle()`` (masking.py:11-38; its asset is not shipped): per-triangle
+    base sampling weights in {0, 0.5, 1} like the reference's area weights."""
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(n_faces, generator=g) > 0.6).float() * torch.tensor([0.5, 1.0])[torch.randint(0, 2, (n_faces,), generator=g)]
+
+
 def random_state_dict(template, seed=7):
     """Fill a ``state_dict``-shaped template (name -> tensor) deterministically, by key name, so the
     reference modules, the oracle and the product modules get identical weights regardless of their

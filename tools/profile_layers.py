@@ -2,7 +2,7 @@
 """Per-layer device times of one eager pass of the hot path, from the library's built-in event
 profiler at detail level 2 (GEMM / depthwise launches tagged with their M, K, N).
 
-    python tools/profile_layers.py [--batch 32] [--generator] [--precision tf32] [--out profiles/x.json]
+    python tools/profile_layers.py [--batch 32] [--generator] [--precision tf32x3] [--out profiles/x.json]
 
 Prints one line per (kernel, shape): launches per step, microseconds per launch, achieved GB/s on
 algorithmic bytes and TFLOP/s — the table the roofline work is steered by."""
@@ -20,7 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--generator", action="store_true")
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "tf32-unfused"])
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32", "tf32-unfused", "tf32x3"])
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
@@ -35,7 +35,7 @@ def main():
     enc = smirk_b200.SmirkEncoder()
     enc.load_state_dict(synth_inputs.random_state_dict(enc.state_dict(), seed=7))
     enc = enc.eval().to(dev)
-    enc.precision = {"fp32": 0, "tf32-unfused": 1, "tf32": 2}[args.precision]
+    enc.precision = {"fp32": 0, "tf32-unfused": 1, "tf32": 2, "tf32x3": 3}[args.precision]
     gen = None
     if args.generator:
         gen = smirk_b200.SmirkGenerator(6, 3, 32, 5)
