@@ -422,3 +422,85 @@ def test_encoder_and_generator_at_batch_256(mods, encoder, generator, asset_root
     ref = generator_ref.generator_forward_ref({k: v.cpu() for k, v in generator.state_dict().items()}, x_sel[:2])
     rel_close(y[sel[:2]], ref, 5e-3, 0)                              # TF32 generator: stated tolerance
     rel_close(gtc(x_sel.to(DEV)), y[sel], 1e-6, 1e-7)                # batch rows independent at B = 256
+
+
+# ----------------------------------------------------------------------- graph lifetime, sub-encoders, masking in the pipeline
+def test_graphs_of_different_batch_sizes_keep_their_own_workspaces(mods, encoder):
+    """capture B = 2, then B = 8 (the module workspaces grow -> new buffers), then re-pack the
+    encoder; the B = 2 graph must still replay correctly: it keeps the workspace and the packed weights it was recorded
+    with alive (rec['keep'])."""
+    import copy
+    import gc
+    from smirk_b200.pipeline import SmirkPipeline
+    fl, rd = mods
+    enc = copy.deepcopy(encoder)
+    enc.precision = 3
+    pipe = SmirkPipeline(enc, fl, rd, None, device=DEV, slots=1)
+    x2, x8 = synth_inputs.images(2, 801).to(DEV), synth_inputs.images(8, 802).to(DEV)
+    eager2 = {k: v.clone() for k, v in pipe.forward(x2).items()}
+    pipe.capture(2)
+    ws_before = enc._ws.buf.data_ptr()
+    eager8 = {k: v.clone() for k, v in pipe.forward(x8).items()}
+    pipe.capture(8)
+    assert enc._ws.buf.data_ptr() != ws_before, "the workspace was expected to grow into a new buffer"
+    with torch.no_grad():
+        enc.shape_encoder.shape_layers[0].bias += 0.0           # bumps the version: the next eager forward re-packs the weights
+    pipe.forward(x8)
+    gc.collect()
+    torch.cuda.empty_cache()
+    scratch = torch.full((64 << 20,), float("nan"), device=DEV)  # would land in any freed workspace
+    o2 = pipe.replay(x2)
+    for k in eager2:
+        assert torch.equal(o2[k], eager2[k]), k
+    o8 = pipe.replay(x8)
+    for k in eager8:
+        assert torch.equal(o8[k], eager8[k]), k
+    del scratch
+
+
+def test_sub_encoders_have_the_reference_forward(encoder):
+    """src/smirk_encoder.py:34-45,66-73,95-110: each sub-encoder is callable on its own and returns its own dict."""
+    img = synth_inputs.images(3, 811).to(DEV)
+    full = encoder(img)
+    p = encoder.pose_encoder(img)
+    s = encoder.shape_encoder(img)
+    e = encoder.expression_encoder(img)
+    assert set(p) == {"pose_params", "cam"} and set(s) == {"shape_params"} and set(e) == {"expression_params", "eyelid_params", "jaw_params"}
+    for d in (p, s, e):
+        for k, v in d.items():
+            rel_close(v, full[k], 1e-6, 1e-7)
+    encoder.train()
+    try:
+        with pytest.raises(RuntimeError, match="train-mode"):
+            encoder(img)                                         # .train() after the first forward must not silently run eval BN
+    finally:
+        encoder.eval()
+
+
+def test_full_cycle_pipeline_with_masking_stage(mods, encoder, generator):
+    """The full cycle with the real masking step (demo.py:138-165) inside the CUDA graph: rendered image and vertices are
+    identical from replay to replay, the masked image is redrawn (device RNG counter advances in-graph), and the
+    generator's input is exactly cat(rendered, masked)."""
+    import copy
+    from smirk_b200.masking import MaskingStage
+    from smirk_b200.pipeline import SmirkPipeline
+    fl, rd = mods
+    gtc = copy.deepcopy(generator); gtc.precision = 1
+    st = MaskingStage(fl.faces_tensor, synth_inputs.face_probabilities(fl.faces_tensor.shape[0]), seed=5)
+    pipe = SmirkPipeline(encoder, fl, rd, gtc, device=DEV, slots=1, masking=st)
+    img, hull = synth_inputs.images(3, 821).to(DEV), synth_inputs.hull_masks(3, 822).to(DEV)
+    a = {k: v.clone() for k, v in pipe.replay(img, hull).items()}
+    b = {k: v.clone() for k, v in pipe.replay(img, hull).items()}
+    assert torch.equal(a["rendered_img"], b["rendered_img"]) and torch.equal(a["vertices"], b["vertices"])
+    assert not torch.equal(a["masked_img"], b["masked_img"]), "the device RNG did not advance between graph replays"
+    m = a["masked_img"]
+    outside = hull.expand(-1, 3, -1, -1) > 0
+    far = torch.nn.functional.max_pool2d(1 - hull, 21, 1, 10) == 0          # pixels the dilated hull does not reach
+    bg = (a["rendered_img"] == 0).all(1, keepdim=True)
+    keep = (far & bg).expand(-1, 3, -1, -1)
+    # outside the dilated hull and off the rendered mesh the image passes through, except at sampled points of mesh parts
+    # the renderer does not draw (scalp, neck), which carry img * noise
+    assert float((m[keep] == img[keep]).float().mean()) > 0.95
+    assert float((m > 0).float().mean()) > 0.1 and outside.any()
+    y = gtc(torch.cat([a["rendered_img"], a["masked_img"]], 1))
+    rel_close(a["reconstructed_img"], y, 1e-6, 1e-7)
