@@ -202,19 +202,32 @@ extern "C" size_t smk_encoder_workspace_bytes(const SmkEncoder* h, int B) {
     return 12 * smk::ws_round((size_t)B * h->max_act * sizeof(float));      // 4 buffers per backbone, 3 concurrent backbones
 }
 
-static int pointwise(const ConvW& c, const float* in, int B, int H, int W, bool relu, const float* res, float* out, cudaStream_t st) {
-    if (c.wt) {
-        smk::TcConv q{};
-        q.in = in; q.ld_in = c.cin; q.B = B; q.H = H; q.W = W; q.Cin = c.cin; q.wt = c.wt; q.wt_lo = c.wt_lo; q.scale = c.scale; q.bias = c.bias;
-        q.N = c.cout; q.K = c.cin; q.mode = 0; q.relu = relu ? 1 : 0; q.res = res; q.ld_res = c.cout; q.res_pad = 0;
-        q.out = out; q.ld_out = c.cout; q.store = 0; q.round_out = c.wt_lo ? 0 : 1;       // 3xTF32 consumers split full fp32 activations themselves
-        return smk::tc_conv(q, st);
+static smk::TcConv tc_problem(const ConvW& c, const float* in, int B, int H, int W, bool relu, const float* res, float* out) {
+    smk::TcConv q{};
+    q.in = in; q.ld_in = c.cin; q.B = B; q.H = H; q.W = W; q.Cin = c.cin; q.wt = c.wt; q.wt_lo = c.wt_lo; q.scale = c.scale; q.bias = c.bias;
+    q.N = c.cout; q.K = c.cin; q.mode = 0; q.relu = relu ? 1 : 0; q.res = res; q.ld_res = c.cout; q.res_pad = 0;
+    q.out = out; q.ld_out = c.cout; q.store = 0; q.round_out = c.wt_lo ? 0 : 1;       // 3xTF32 consumers split full fp32 activations themselves
+    return q;
+}
+
+// One 1x1 convolution for n = 1 or 2 backbones of identical structure (c[k], in[k], res[k], out[k]).  On the tensor-core
+// path a pair shares ONE launch (gemm_tc.cu, TcMaps): half the launches and twice the tiles per launch for layers that
+// sit on the launch/latency floor.
+static int pointwise(int n, const ConvW* const* c, float* const* in, int B, int H, int W, bool relu, float* const* res, float* const* out, cudaStream_t st) {
+    if (c[0]->wt) {
+        smk::TcConv q0 = tc_problem(*c[0], in[0], B, H, W, relu, res ? res[0] : nullptr, out[0]);
+        if (n == 1) return smk::tc_conv(q0, st);
+        smk::TcConv q1 = tc_problem(*c[1], in[1], B, H, W, relu, res ? res[1] : nullptr, out[1]);
+        return smk::tc_conv(q0, st, &q1);
     }
-    ConvProblem p{};
-    p.in = in; p.ld_in = c.cin; p.B = B; p.H = H; p.W = W; p.Cin = c.cin;
-    p.w = c.w; p.scale = c.scale; p.bias = c.bias; p.N = c.cout; p.K = c.cin; p.mode = 0; p.relu = relu ? 1 : 0;
-    p.res = res; p.ld_res = c.cout; p.out = out; p.ld_out = c.cout; p.shuffle = 0;
-    return smk::conv_gemm(p, st);
+    for (int k = 0; k < n; ++k) {
+        ConvProblem p{};
+        p.in = in[k]; p.ld_in = c[k]->cin; p.B = B; p.H = H; p.W = W; p.Cin = c[k]->cin;
+        p.w = c[k]->w; p.scale = c[k]->scale; p.bias = c[k]->bias; p.N = c[k]->cout; p.K = c[k]->cin; p.mode = 0; p.relu = relu ? 1 : 0;
+        p.res = res ? res[k] : nullptr; p.ld_res = c[k]->cout; p.out = out[k]; p.ld_out = c[k]->cout; p.shuffle = 0;
+        if (int rc = smk::conv_gemm(p, st)) return rc;
+    }
+    return 0;
 }
 
 extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B, float* pose_cam, float* shape,
@@ -255,49 +268,81 @@ extern "C" int smk_encoder_forward(const SmkEncoder* h, const float* img, int B,
         for (int s = 0; s < 2; ++s) SMK_CHECK_CUDA(cudaStreamWaitEvent(fk.side[s], fk.fork, 0));
     }
     int rc = 0;                                   // first error; the side streams are joined on every path
-    for (int i = 0; i < 3 && !rc; ++i) {
-        if (!h->present[i]) continue;
-        const Backbone& bb = h->bb[i];
-        cudaStream_t st = (i == 0 || !concurrent) ? main_st : fk.side[i - 1];
-        float* const* buf = bufs[i];
-        float *x = buf[0], *y = buf[1], *e = buf[2], *d = buf[3];
+    // Work units: the two "large" backbones (shape, expression) have the same layer list, so on the tensor-core path they
+    // advance in lock step and every layer of the pair is ONE launch; the small (pose) backbone is its own unit.
+    static const int pair_env = []() { const char* e = getenv("SMK_ENC_PAIR"); return e ? atoi(e) : 1; }();
+    const bool pair = pair_env && h->precision >= 1 && h->present[1] && h->present[2];
+    struct Unit { int n; int idx[2]; cudaStream_t st; };
+    Unit units[3]; int n_units = 0;
+    if (h->present[0]) units[n_units++] = Unit{1, {0, 0}, main_st};
+    if (pair) units[n_units++] = Unit{2, {1, 2}, concurrent ? fk.side[0] : main_st};
+    else for (int i = 1; i < 3; ++i) if (h->present[i]) units[n_units++] = Unit{1, {i, i}, concurrent ? fk.side[i - 1] : main_st};
+    if (!h->present[0] && n_units > 0) units[0].st = main_st;                        // a lone unit runs on the caller's stream
+    for (int u = 0; u < n_units && !rc; ++u) {
+        const int n = units[u].n;
+        cudaStream_t st = units[u].st;
+        const Backbone* bb[2]; float *x[2], *y[2], *e[2], *d[2];
+        for (int k = 0; k < n; ++k) {
+            const int i = units[u].idx[k];
+            bb[k] = &h->bb[i]; x[k] = bufs[i][0]; y[k] = bufs[i][1]; e[k] = bufs[i][2]; d[k] = bufs[i][3];
+        }
         int res = 112;
         size_t first = 0;
         if (fuse_stem) {
-            const Block& b0 = bb.blocks[0];
-            rc = smk::stem_ds(img, B, 224, 224, bb.stem.w, bb.stem.scale, bb.stem.bias, b0.dw.w, b0.dw.scale, b0.dw.bias,
-                              b0.pw_f32.w, b0.pw_f32.scale, b0.pw_f32.bias, b0.stride, h->x3 ? 0 : 1, x, st);
+            const Block& b0 = bb[0]->blocks[0];
+            smk::StemDsProblem sp[2];
+            for (int k = 0; k < n; ++k) {
+                const Block& bk = bb[k]->blocks[0];
+                sp[k] = smk::StemDsProblem{bb[k]->stem.w, bb[k]->stem.scale, bb[k]->stem.bias, bk.dw.w, bk.dw.scale, bk.dw.bias,
+                                           bk.pw_f32.w, bk.pw_f32.scale, bk.pw_f32.bias, x[k]};
+            }
+            rc = smk::stem_ds(img, B, 224, 224, sp, n, b0.stride, h->x3 ? 0 : 1, st);
             res = 112 / b0.stride; first = 1;
         }
-        for (size_t bi = first; bi < bb.blocks.size() && !rc; ++bi) {
-            const Block& b = bb.blocks[bi];
-            int ro = (res + b.stride - 1) / b.stride;
-            if (b.kind == DS) {
-                rc = smk::dwconv3x3(x, B, res, res, b.cin, b.stride, b.dw.w, b.dw.scale, b.dw.bias, d, st, h->precision == 1 && !h->x3);
-                if (!rc) rc = pointwise(b.pw, d, B, ro, ro, false, b.skip ? x : nullptr, y, st);
-            } else if (b.kind == IR) {
+        for (size_t bi = first; bi < bb[0]->blocks.size() && !rc; ++bi) {
+            const Block* b[2] = {&bb[0]->blocks[bi], &bb[n - 1]->blocks[bi]};
+            const Block& b0 = *b[0];
+            const int ro = (res + b0.stride - 1) / b0.stride;
+            const bool rnd = h->precision == 1 && !h->x3;
+            const ConvW* pw[2] = {&b[0]->pw, &b[1]->pw};
+            const ConvW* pwl[2] = {&b[0]->pwl, &b[1]->pwl};
+            if (b0.kind == DS) {
+                for (int k = 0; k < n && !rc; ++k)
+                    rc = smk::dwconv3x3(x[k], B, res, res, b[k]->cin, b[k]->stride, b[k]->dw.w, b[k]->dw.scale, b[k]->dw.bias, d[k], st, rnd);
+                if (!rc) rc = pointwise(n, pw, d, B, ro, ro, false, b0.skip ? x : nullptr, y, st);
+            } else if (b0.kind == IR) {
                 // The 7x7 layers (a 16x16 window holds 81 useful pixels, 49 outputs) run 3 % faster end to end as
                 // 1x1 GEMM + depthwise kernels; every other resolution wins fused (profiles/r01_footprint_sweep.txt).
                 static const int xdw_min_res = []() { const char* e = getenv("SMK_XDW_MIN_RES"); return e ? atoi(e) : 8; }();
-                if (h->fuse_xdw && b.pw.wt && res >= xdw_min_res) {
+                if (h->fuse_xdw && b0.pw.wt && res >= xdw_min_res) {
                     // expand 1x1 + depthwise 3x3 in one kernel: the expanded tensor never leaves the SM
-                    smk::XdwConv q{};
-                    q.x = x; q.B = B; q.H = res; q.W = res; q.Cin = b.cin; q.w1t = b.pw.wt; q.w1t_lo = b.pw.wt_lo; q.scale1 = b.pw.scale; q.bias1 = b.pw.bias;
-                    q.mid = b.mid; q.wdw = b.dw.w; q.scale2 = b.dw.scale; q.bias2 = b.dw.bias; q.stride = b.stride; q.round_out = h->x3 ? 0 : 1; q.out = d;
-                    rc = smk::xdw_conv(q, st);
+                    smk::XdwConv q[2];
+                    for (int k = 0; k < n; ++k) {
+                        q[k] = smk::XdwConv{};
+                        q[k].x = x[k]; q[k].B = B; q[k].H = res; q[k].W = res; q[k].Cin = b[k]->cin; q[k].w1t = b[k]->pw.wt; q[k].w1t_lo = b[k]->pw.wt_lo;
+                        q[k].scale1 = b[k]->pw.scale; q[k].bias1 = b[k]->pw.bias; q[k].mid = b[k]->mid; q[k].wdw = b[k]->dw.w;
+                        q[k].scale2 = b[k]->dw.scale; q[k].bias2 = b[k]->dw.bias; q[k].stride = b[k]->stride; q[k].round_out = h->x3 ? 0 : 1; q[k].out = d[k];
+                    }
+                    rc = smk::xdw_conv(q[0], st, n == 2 ? &q[1] : nullptr);
                 } else {
-                    rc = pointwise(b.pw, x, B, res, res, true, nullptr, e, st);
-                    if (!rc) rc = smk::dwconv3x3(e, B, res, res, b.mid, b.stride, b.dw.w, b.dw.scale, b.dw.bias, d, st, h->precision == 1 && !h->x3);
+                    rc = pointwise(n, pw, x, B, res, res, true, nullptr, e, st);
+                    for (int k = 0; k < n && !rc; ++k)
+                        rc = smk::dwconv3x3(e[k], B, res, res, b[k]->mid, b[k]->stride, b[k]->dw.w, b[k]->dw.scale, b[k]->dw.bias, d[k], st, rnd);
                 }
-                if (!rc) rc = pointwise(b.pwl, d, B, ro, ro, false, b.skip ? x : nullptr, y, st);
+                if (!rc) rc = pointwise(n, pwl, d, B, ro, ro, false, b0.skip ? x : nullptr, y, st);
             } else {
-                rc = pointwise(b.pw, x, B, res, res, true, nullptr, y, st);
+                rc = pointwise(n, pw, x, B, res, res, true, nullptr, y, st);
             }
             if (rc) break;
-            std::swap(x, y);
+            for (int k = 0; k < n; ++k) std::swap(x[k], y[k]);
             res = ro;
         }
-        if (!rc) rc = smk::gap_linear(x, B, res * res, bb.feat, bb.head_w, bb.head_b, bb.n_out, bb.codes, y, outs[i], st);
+        if (!rc) {                              // global average pool + head + clamps: one launch per unit
+            smk::GapHeadProblem gp[2];
+            for (int k = 0; k < n; ++k)
+                gp[k] = smk::GapHeadProblem{x[k], bb[k]->head_w, bb[k]->head_b, bb[k]->codes, outs[units[u].idx[k]], bb[k]->n_out};
+            rc = smk::gap_head(gp, n, B, res * res, bb[0]->feat, st);
+        }
     }
     for (int s = 0; s < 2 && concurrent; ++s) {   // join even after an error so a capturing stream is left consistent
         cudaError_t e1 = cudaEventRecord(fk.join[s], fk.side[s]);

@@ -46,20 +46,26 @@ struct TcArgs {
     int H, W;                      // output spatial dims (im2col tile origin decode; shuffle / padded stores)
     int cpb;                       // k-blocks per filter tap (Cin / 32) for im2col
     int lc;                        // im2col lower corner (-1: zero padding 1; 0: input already reflection-padded)
-    const float* scale; const float* bias;
-    const float* res; int ld_res; int res_pad;   // residual (optionally read from the interior of a padded buffer)
+    // Two problems of identical shape may share one launch (the encoder's two "large" backbones run the same layer
+    // list on different weights and activations): tiles [0, n_tiles_g) belong to problem 0, [n_tiles_g, 2 n_tiles_g) to
+    // problem 1, each with its own tensor maps (TcMaps) and epilogue pointers.  Twice the work per launch for kernels
+    // that sit on the launch/latency floor.
+    int n_tiles_g;                 // tiles per problem (= n_tiles when there is only one)
+    const float* scale[2]; const float* bias[2];
+    const float* res[2]; int ld_res; int res_pad;   // residual (optionally read from the interior of a padded buffer)
     int relu;
-    float* out; int ld_out;
+    float* out[2]; int ld_out;
     int store;                     // 0 plain, 1 pixel-shuffle (N = 4*Cout), 2 interior of a (H+2)x(W+2) padded buffer,
                                    // 3 fused head: out[b, co, h, w] = sigmoid(head_b[co] + sum_n act[m, n] * head_w[n][co]) (NCHW, N <= 32)
     int round_out;                 // 1: round the stored activations to TF32 (round-to-nearest) for the next tensor-core layer
     const float* head_w; const float* head_b; int head_c;      // store 3: 1x1 head weights [N][head_c], bias [head_c], head_c <= 4
 };
 
+struct TcMaps { CUtensorMap a[2], b[2], blo[2]; };       // per problem: activations, weights (TF32 heads), weight tails (3xTF32)
+
 template <int BN, int STAGES, int MINB, bool PERSIST, int X3>
 __global__ void __launch_bounds__(NUM_THREADS, MINB)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
-               const TcArgs a) {
+gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcArgs a) {
     // Output tiles (128 rows x BN columns) are strided over the grid.
     //   PERSIST = true : grid = resident CTAs; the smem ring runs across tile boundaries and the accumulator is
     //                    double-buffered in TMEM, so the TMA loads and MMAs of tile i+1 overlap the epilogue of
@@ -103,9 +109,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-        if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
+        const int g0 = (!PERSIST && (int)blockIdx.x >= a.n_tiles_g) ? 1 : 0;
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mp.a[g0]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mp.b[g0]) : "memory");
+        if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&mp.blo[g0]) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&split[s], 4); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -125,7 +132,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // ===== TMA producer =====
             int it = 0;
             for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
-                const int tm = t / a.tiles_n, tn = t - tm * a.tiles_n;
+                const int g = t >= a.n_tiles_g ? 1 : 0, tt = t - g * a.n_tiles_g;
+                const CUtensorMap* tmA = &mp.a[g]; const CUtensorMap* tmB = &mp.b[g]; const CUtensorMap* tmBlo = &mp.blo[g];
+                const int tm = tt / a.tiles_n, tn = tt - tm * a.tiles_n;
                 const int m0 = tm * BM, n0 = tn * BN;
                 int q0 = 0, p0 = 0, img = 0;
                 if (a.mode == 1) { int hw = a.H * a.W; img = m0 / hw; int r = m0 - img * hw; p0 = r / a.W; q0 = r - p0 * a.W; }
@@ -135,15 +144,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint8_t* sa = smem + s * STAGE_BYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
                     mbar_expect_tx(&full[s], (uint32_t)(HALF_STAGE_BYTES + (X3 ? B_STAGE_BYTES : 0)));
-                    if (X3) tma_load_2d(&tmBlo, sa + BLO_OFF, &full[s], kb * BK, n0);
+                    if (X3) tma_load_2d(tmBlo, sa + BLO_OFF, &full[s], kb * BK, n0);
                     if (a.mode == 0) {
-                        tma_load_2d(&tmA, sa, &full[s], kb * BK, m0);
+                        tma_load_2d(tmA, sa, &full[s], kb * BK, m0);
                     } else {
                         int tap = kb / a.cpb, ch = kb - tap * a.cpb;
                         int r = tap / 3, sx = tap - r * 3;
-                        tma_load_im2col(&tmA, sa, &full[s], ch * BK, q0 + a.lc, p0 + a.lc, img, (uint16_t)sx, (uint16_t)r);
+                        tma_load_im2col(tmA, sa, &full[s], ch * BK, q0 + a.lc, p0 + a.lc, img, (uint16_t)sx, (uint16_t)r);
                     }
-                    tma_load_2d(&tmB, sb, &full[s], kb * BK, n0);
+                    tma_load_2d(tmB, sb, &full[s], kb * BK, n0);
                 }
             }
         }
@@ -237,7 +246,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int sub = lane >> 3, jj = lane & 7;              // phase-2 role: row-in-group, 16-byte chunk
         int tc = 0;
         for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++tc) {
-            const int tm = t / a.tiles_n, tn = t - tm * a.tiles_n;
+            const int g = t >= a.n_tiles_g ? 1 : 0, tt = t - g * a.n_tiles_g;
+            const float* __restrict__ g_scale = a.scale[g]; const float* __restrict__ g_bias = a.bias[g];
+            const float* __restrict__ g_res = a.res[g]; float* __restrict__ g_out = a.out[g];
+            const int tm = tt / a.tiles_n, tn = tt - tm * a.tiles_n;
             const int m0 = tm * BM, n0 = tn * BN;
             const int buf = tc & 1;
             int opix[8], rpix[8];                              // destination / residual pixel of my 8 phase-2 rows (-1: past M)
@@ -276,8 +288,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
                 const int nc = n + jj * 4;                     // my 4 columns
                 if (nc < a.N) {
-                    const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + nc));
-                    const float4 bi = __ldg(reinterpret_cast<const float4*>(a.bias + nc));
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(g_scale + nc));
+                    const float4 bi = __ldg(reinterpret_cast<const float4*>(g_bias + nc));
                     int col = nc, pix_off = 0;
                     if (a.store == 1) {                        // ConvTranspose2d k2 s2: n = (dy*2+dx)*Cout + co
                         const int cout = a.N >> 2, q = nc / cout;
@@ -290,8 +302,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const float4 x = *reinterpret_cast<const float4*>(slab + r * 128 + ((jj ^ (r & 7)) << 4));
                         float4 o;
                         o.x = fmaf(x.x, sc.x, bi.x); o.y = fmaf(x.y, sc.y, bi.y); o.z = fmaf(x.z, sc.z, bi.z); o.w = fmaf(x.w, sc.w, bi.w);
-                        if (a.res) {
-                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.res + (size_t)rpix[i] * a.ld_res + nc));
+                        if (g_res) {
+                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(g_res + (size_t)rpix[i] * a.ld_res + nc));
                             o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
                         }
                         if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
@@ -315,12 +327,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (jj == 0) {
                                 const int hw = a.H * a.W, b = opix[i] / hw, rem = opix[i] - b * hw;
                                 for (int co = 0; co < a.head_c; ++co)
-                                    a.out[((size_t)b * a.head_c + co) * hw + rem] = 1.f / (1.f + __expf(-(acc[co] + __ldg(a.head_b + co))));
+                                    g_out[((size_t)b * a.head_c + co) * hw + rem] = 1.f / (1.f + __expf(-(acc[co] + __ldg(a.head_b + co))));
                             }
                             continue;
                         }
                         if (a.round_out) { o.x = smk::round_tf32(o.x); o.y = smk::round_tf32(o.y); o.z = smk::round_tf32(o.z); o.w = smk::round_tf32(o.w); }
-                        *reinterpret_cast<float4*>(a.out + (size_t)(opix[i] + pix_off) * a.ld_out + col) = o;
+                        *reinterpret_cast<float4*>(g_out + (size_t)(opix[i] + pix_off) * a.ld_out + col) = o;
                     }
                 }
                 __syncwarp();
@@ -410,7 +422,7 @@ int encode_im2col(CUtensorMap* map, const float* base, int B, int Hin, int Win, 
 }
 
 template <int BN, int STAGES, int MINB, bool PERSIST, int X3 = 0>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a_in, cudaStream_t st, const CUtensorMap* tmBlo = nullptr) {
+int launch(const TcMaps& mp, const TcArgs& a_in, cudaStream_t st, int groups) {
     constexpr size_t stage = X3 == 1 ? 2 * (A_STAGE_BYTES + BN * BKB) : (X3 == 2 ? A_STAGE_BYTES + 2 * BN * BKB : A_STAGE_BYTES + BN * BKB);
     constexpr size_t smem = (size_t)STAGES * stage + (PERSIST ? SLAB_BYTES : 0) + 1024 + 256;
     static_assert(MINB * (smem + 1024) <= 228 * 1024, "shared memory budget of MINB resident CTAs");
@@ -426,9 +438,10 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a_in, c
     }
     TcArgs a = a_in;
     a.tiles_n = cdiv(a.N, BN);
-    a.n_tiles = cdiv(a.M, BM) * a.tiles_n;
+    a.n_tiles_g = cdiv(a.M, BM) * a.tiles_n;
+    a.n_tiles = groups * a.n_tiles_g;
     dim3 grid((unsigned)(PERSIST ? std::min(a.n_tiles, MINB * 148) : a.n_tiles));
-    SMK_LAUNCH((gemm_tc_kernel<BN, STAGES, MINB, PERSIST, X3>), dim3(grid), dim3(NUM_THREADS), smem, st, tmA, tmB, tmBlo ? *tmBlo : tmB, a);
+    SMK_LAUNCH((gemm_tc_kernel<BN, STAGES, MINB, PERSIST, X3>), dim3(grid), dim3(NUM_THREADS), smem, st, mp, a);
     SMK_CHECK_LAUNCH();
     return 0;
 }
@@ -437,12 +450,17 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a_in, c
 
 int tc_init() { return load_driver_fns(); }
 
-int tc_conv(const TcConv& p, cudaStream_t st) {
+int tc_conv(const TcConv& p, cudaStream_t st, const TcConv* p2) {
     if (int rc = load_driver_fns()) return rc;
     const int M = p.B * p.H * p.W;
+    const int groups = p2 ? 2 : 1;
     SMK_REQUIRE(p.N % 4 == 0 && p.K % 4 == 0 && p.ld_in % 4 == 0 && p.ld_out % 4 == 0, "tc_conv: N, K, ld must be multiples of 4");
     SMK_REQUIRE(p.mode == 0 || (p.Cin % BK == 0 && p.K == 9 * p.Cin), "tc_conv: 3x3 mode needs Cin %% 32 == 0 (got %d)", p.Cin);
     SMK_REQUIRE(p.store != 1 || ((p.N / 4) % 32 == 0), "tc_conv: pixel-shuffle store needs Cout %% 32 == 0");
+    SMK_REQUIRE(!p2 || (p2->B == p.B && p2->H == p.H && p2->W == p.W && p2->Cin == p.Cin && p2->N == p.N && p2->K == p.K && p2->mode == p.mode &&
+                        p2->relu == p.relu && p2->ld_in == p.ld_in && p2->ld_out == p.ld_out && p2->ld_res == p.ld_res && p2->store == p.store &&
+                        p2->res_pad == p.res_pad && p2->round_out == p.round_out && !p2->wt_lo == !p.wt_lo && !p2->res == !p.res && p.store != 3),
+                "tc_conv: paired problems must have identical shapes and epilogue options");
     int BN = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
     // Wide layers (N >= 256: the generator's 28^2 / 14^2 convolutions, 75 % of its FLOPs): a 128 x 256 tile halves the
     // A-operand bytes the tensor core pulls from shared memory per FLOP.  TF32 operands are 4 bytes, so at BN = 128 the
@@ -462,62 +480,67 @@ int tc_conv(const TcConv& p, cudaStream_t st) {
         // (narrowing is off by default: fewer, wider tiles re-read A less often, and in the concurrent pipeline idle SMs
         //  are filled by other kernels anyway; SMK_TC_NARROW=148 restores the latency-oriented choice.)
         static const int narrow_target = []() { const char* e = getenv("SMK_TC_NARROW"); return e ? atoi(e) : 0; }();
-        while (BN > 32 && (long)cdiv(M, BM) * cdiv(p.N, BN) < narrow_target) BN >>= 1;
+        while (BN > 32 && (long)groups * cdiv(M, BM) * cdiv(p.N, BN) < narrow_target) BN >>= 1;
         static const int deep_small_on = []() { const char* e = getenv("SMK_TC_DEEP_SMALL"); return e ? atoi(e) : 0; }();
-        deep_small = deep_small_on && (long)cdiv(M, BM) * cdiv(p.N, BN) <= 2 * 148;
+        deep_small = deep_small_on && (long)groups * cdiv(M, BM) * cdiv(p.N, BN) <= 2 * 148;
     }
-    CUtensorMap tmA, tmB;
+    TcMaps mp;
     TcArgs a{};
     a.M = M; a.N = p.N; a.nkb = cdiv(p.K, BK); a.mode = p.mode == 0 ? 0 : 1; a.H = p.H; a.W = p.W;
     a.cpb = p.mode == 0 ? 1 : p.Cin / BK; a.lc = p.mode == 2 ? 0 : -1;
-    a.scale = p.scale; a.bias = p.bias; a.res = p.res; a.ld_res = p.ld_res; a.res_pad = p.res_pad; a.relu = p.relu;
-    a.out = p.out; a.ld_out = p.ld_out; a.store = p.store; a.round_out = p.round_out;
+    a.ld_res = p.ld_res; a.res_pad = p.res_pad; a.relu = p.relu;
+    a.ld_out = p.ld_out; a.store = p.store; a.round_out = p.round_out;
     a.head_w = p.head_w; a.head_b = p.head_b; a.head_c = p.head_c;
     SMK_REQUIRE(p.store != 3 || (p.N <= 32 && p.head_w && p.head_b && p.head_c >= 1 && p.head_c <= 4 && !p.res),
                 "tc_conv: the fused 1x1 head needs N <= 32 (one column tile) and 1..4 head channels");
-    if (p.mode == 0) {
-        if (int rc = encode_2d(&tmA, p.in, (uint64_t)M, (uint64_t)p.K, (uint64_t)p.ld_in, BM)) return rc;
-    } else if (p.mode == 1) {
-        if (int rc = encode_im2col(&tmA, p.in, p.B, p.H, p.W, p.Cin, p.ld_in, 1)) return rc;
-    } else {                                            // input buffer is [B, H+2, W+2, C], already reflection padded
-        if (int rc = encode_im2col(&tmA, p.in, p.B, p.H + 2, p.W + 2, p.Cin, p.ld_in, 0)) return rc;
+    SMK_REQUIRE(!p.wt_lo || (p.mode == 0 && p.store == 0), "tc_conv: the 3xTF32 path covers plain 1x1 convolutions / GEMMs");
+    for (int g = 0; g < groups; ++g) {
+        const TcConv& q = g ? *p2 : p;
+        a.scale[g] = q.scale; a.bias[g] = q.bias; a.res[g] = q.res; a.out[g] = q.out;
+        if (q.mode == 0) {
+            if (int rc = encode_2d(&mp.a[g], q.in, (uint64_t)M, (uint64_t)q.K, (uint64_t)q.ld_in, BM)) return rc;
+        } else if (q.mode == 1) {
+            if (int rc = encode_im2col(&mp.a[g], q.in, q.B, q.H, q.W, q.Cin, q.ld_in, 1)) return rc;
+        } else {                                            // input buffer is [B, H+2, W+2, C], already reflection padded
+            if (int rc = encode_im2col(&mp.a[g], q.in, q.B, q.H + 2, q.W + 2, q.Cin, q.ld_in, 0)) return rc;
+        }
+        if (int rc = encode_2d(&mp.b[g], q.wt, (uint64_t)q.N, (uint64_t)q.K, (uint64_t)q.K, (uint32_t)BN)) return rc;
+        if (q.wt_lo) { if (int rc = encode_2d(&mp.blo[g], q.wt_lo, (uint64_t)q.N, (uint64_t)q.K, (uint64_t)q.K, (uint32_t)BN)) return rc; }
+        else mp.blo[g] = mp.b[g];
     }
-    if (int rc = encode_2d(&tmB, p.wt, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, (uint32_t)BN)) return rc;
+    if (groups == 1) { mp.a[1] = mp.a[0]; mp.b[1] = mp.b[0]; mp.blo[1] = mp.blo[0]; a.scale[1] = a.scale[0]; a.bias[1] = a.bias[0]; a.res[1] = a.res[0]; a.out[1] = a.out[0]; }
     {
         const double cin_eff = p.mode == 0 ? p.K : p.Cin;
         const char* tag = p.mode == 0 ? (p.store == 1 ? "upconv_gemm_tc" : (p.wt_lo ? "pw_gemm_tc3x" : "pw_gemm_tc")) : "conv3x3_gemm_tc";
-        if (g_prof_detail) tag = prof_shape_tag(tag, M, p.K, p.N);
+        if (g_prof_detail) tag = prof_shape_tag(tag, (long)groups * M, p.K, p.N);
         SMK_TAG(tag,
-                4.0 * ((double)M * cin_eff + (double)p.K * p.N + (double)M * p.N * (p.res ? 2 : 1) + 2.0 * p.N),
-                2.0 * (double)M * p.N * p.K, st);
+                groups * 4.0 * ((double)M * cin_eff + (double)p.K * p.N + (double)M * p.N * (p.res ? 2 : 1) + 2.0 * p.N),
+                groups * 2.0 * (double)M * p.N * p.K, st);
     }
     if (p.wt_lo) {                                      // 3xTF32: fp32-equivalent arithmetic (encoder precision 3)
-        SMK_REQUIRE(p.mode == 0 && p.store == 0, "tc_conv: the 3xTF32 path covers plain 1x1 convolutions / GEMMs");
-        CUtensorMap tmBlo;
-        if (int rc = encode_2d(&tmBlo, p.wt_lo, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.K, (uint32_t)BN)) return rc;
         // tails of the activations in tensor memory (default) or in shared memory (SMK_X3_TMEM=0: the first, larger-footprint cut)
         static const int x3_tmem = []() { const char* e = getenv("SMK_X3_TMEM"); return e ? atoi(e) : 1; }();
         if (x3_tmem) {
-            if (BN == 32) return launch<32, 2, 4, false, 2>(tmA, tmB, a, st, &tmBlo);
-            if (BN == 64) return launch<64, 2, 3, false, 2>(tmA, tmB, a, st, &tmBlo);
-            return launch<128, 2, 2, false, 2>(tmA, tmB, a, st, &tmBlo);
+            if (BN == 32) return launch<32, 2, 4, false, 2>(mp, a, st, groups);
+            if (BN == 64) return launch<64, 2, 3, false, 2>(mp, a, st, groups);
+            return launch<128, 2, 2, false, 2>(mp, a, st, groups);
         }
-        if (BN == 32) return launch<32, 2, 2, false, 1>(tmA, tmB, a, st, &tmBlo);
-        if (BN == 64) return launch<64, 2, 2, false, 1>(tmA, tmB, a, st, &tmBlo);
-        return launch<128, 2, 1, false, 1>(tmA, tmB, a, st, &tmBlo);
+        if (BN == 32) return launch<32, 2, 2, false, 1>(mp, a, st, groups);
+        if (BN == 64) return launch<64, 2, 2, false, 1>(mp, a, st, groups);
+        return launch<128, 2, 1, false, 1>(mp, a, st, groups);
     }
-    if (deep_small && BN == 32) return launch<32, 8, 1, false>(tmA, tmB, a, st);
-    if (deep_small && BN == 64) return launch<64, 8, 1, false>(tmA, tmB, a, st);
+    if (deep_small && BN == 32) return launch<32, 8, 1, false>(mp, a, st, groups);
+    if (deep_small && BN == 64) return launch<64, 8, 1, false>(mp, a, st, groups);
     static const int persist_mode = []() { const char* e = getenv("SMK_TC_PERSIST"); return e ? atoi(e) : -1; }();   // -1 auto, 0 never, 1 always
-    const long n_tiles = (long)cdiv(M, BM) * cdiv(p.N, BN);
+    const long n_tiles = (long)groups * cdiv(M, BM) * cdiv(p.N, BN);
     // 3x3 convolutions (deep K): persistent CTAs for the narrow-N layers and for the few-tile 14x14 layers;
     // the wide-N layers are bound by the shared-memory fill rate either way and keep two single-tile CTAs per SM.
     const bool persist = persist_mode >= 0 ? persist_mode != 0 : (p.mode != 0 && (BN <= 64 || n_tiles <= 2 * 148));
-    if (BN == 256) return launch<256, 4, 1, true>(tmA, tmB, a, st);
+    if (BN == 256) return launch<256, 4, 1, true>(mp, a, st, groups);
     if (persist) {
-        if (BN == 32) return launch<32, 4, 2, true>(tmA, tmB, a, st);
-        if (BN == 64) return launch<64, 3, 2, true>(tmA, tmB, a, st);
-        return a.nkb > 8 ? launch<128, 5, 1, true>(tmA, tmB, a, st) : launch<128, 2, 2, true>(tmA, tmB, a, st);
+        if (BN == 32) return launch<32, 4, 2, true>(mp, a, st, groups);
+        if (BN == 64) return launch<64, 3, 2, true>(mp, a, st, groups);
+        return a.nkb > 8 ? launch<128, 5, 1, true>(mp, a, st, groups) : launch<128, 2, 2, true>(mp, a, st, groups);
     }
     // One tile per CTA, 2-stage ring: 41-66 KB per CTA, so 3-5 CTAs of this kernel — or CTAs of the other
     // backbones' and batches' kernels — share an SM and hide each other's prologue/epilogue.  Deeper rings
@@ -525,9 +548,9 @@ int tc_conv(const TcConv& p, cudaStream_t st) {
     // 5 % end to end for the same co-residency reason as above.
     static const int shallow_nkb = []() { const char* e = getenv("SMK_TC_SHALLOW_NKB"); return e ? atoi(e) : (1 << 30); }();
     const bool shallow = a.nkb <= shallow_nkb;
-    if (BN == 32) return shallow ? launch<32, 2, 5, false>(tmA, tmB, a, st) : launch<32, 4, 2, false>(tmA, tmB, a, st);
-    if (BN == 64) return shallow ? launch<64, 2, 4, false>(tmA, tmB, a, st) : launch<64, 4, 2, false>(tmA, tmB, a, st);
-    return shallow ? launch<128, 2, 3, false>(tmA, tmB, a, st) : launch<128, 3, 2, false>(tmA, tmB, a, st);
+    if (BN == 32) return shallow ? launch<32, 2, 5, false>(mp, a, st, groups) : launch<32, 4, 2, false>(mp, a, st, groups);
+    if (BN == 64) return shallow ? launch<64, 2, 4, false>(mp, a, st, groups) : launch<64, 4, 2, false>(mp, a, st, groups);
+    return shallow ? launch<128, 2, 3, false>(mp, a, st, groups) : launch<128, 3, 2, false>(mp, a, st, groups);
 }
 
 int reflect_halo(float* buf, int B, int H, int W, int C, cudaStream_t st) {

@@ -22,7 +22,8 @@ struct TcConv {
 };
 
 int tc_init();                                              // resolves the driver's tensor-map encoders
-int tc_conv(const TcConv& p, cudaStream_t st);
+// p2 (optional): a second problem of identical shape sharing the launch (tiles of both in one grid).
+int tc_conv(const TcConv& p, cudaStream_t st, const TcConv* p2 = nullptr);
 int reflect_halo(float* buf, int B, int H, int W, int C, cudaStream_t st);
 
 }  // namespace smk

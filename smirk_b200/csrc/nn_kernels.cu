@@ -268,6 +268,52 @@ head_linear_kernel(const float* __restrict__ pooled, int C, const float* __restr
     }
 }
 
+// Global average pool + linear head + clamps in ONE launch for one or two backbones (blockIdx.z): every CTA pools its
+// image's feature map into shared memory (the map is L2-resident: 188 KB at 7x7x960) and computes 32 head outputs, one
+// warp per output (smirk_encoder.py:34-45,66-73,95-110).  Replaces gap_kernel + head_linear_kernel: 6 launches per
+// encoder pass become 2.
+struct GapHead { const float* feat[2]; const float* w[2]; const float* bias[2]; const uint8_t* codes[2]; float* out[2]; int n_out[2]; };
+__global__ void __launch_bounds__(256)
+gap_head_kernel(const __grid_constant__ GapHead g, int HW, int C) {
+    extern __shared__ float pooled[];                 // [C]
+    pdl_sync();
+    const int q = blockIdx.z, b = blockIdx.x;
+    const int n_out = g.n_out[q];
+    if ((int)blockIdx.y * 32 >= n_out) return;
+    const float* f = g.feat[q] + (size_t)b * HW * C;
+    const float inv = 1.f / (float)HW;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int p = 0;
+        for (; p + 4 <= HW; p += 4) {
+            s0 += f[(size_t)p * C + c]; s1 += f[(size_t)(p + 1) * C + c]; s2 += f[(size_t)(p + 2) * C + c]; s3 += f[(size_t)(p + 3) * C + c];
+        }
+        for (; p < HW; ++p) s0 += f[(size_t)p * C + c];
+        pooled[c] = ((s0 + s1) + (s2 + s3)) * inv;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* w = g.w[q]; const float* bias = g.bias[q]; const uint8_t* codes = g.codes[q];
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        const int o = blockIdx.y * 32 + warp * 4 + j;
+        if (o >= n_out) break;
+        const float* wr = w + (size_t)o * C;
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32) acc = fmaf(pooled[c], __ldg(wr + c), acc);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+        if (lane == 0) {
+            float v = acc + bias[o];
+            const int code = codes ? codes[o] : 0;
+            if (code == 1) v = fminf(fmaxf(v, 0.f), 1.f);
+            else if (code == 2) v = fmaxf(v, 0.f);
+            else if (code == 3) v = fminf(fmaxf(v, -0.2f), 0.2f);
+            g.out[q][(size_t)b * n_out + o] = v;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128)
 stem_conv_kernel(const float* __restrict__ img, int B, int H, int W, int Ho, int Wo, int pad,
                  const float* __restrict__ w /*[27][16]*/, const float* __restrict__ scale,
@@ -521,16 +567,20 @@ namespace {
 constexpr int SD_T = 16, SD_ST = SD_T + 2;                 // stem-resolution tile edge, with halo
 constexpr int SD_PR = 2 * SD_ST + 1;                       // image patch rows / cols (37)
 constexpr int SD_PP = 20;                                  // patch row pitch per column parity (19 even + 18 odd columns)
-struct StemDs {
-    const float* stem_w; const float* stem_s; const float* stem_b;      // [27][16], [16], [16]
-    const float* dw_w; const float* dw_s; const float* dw_b;            // [9][16]
-    const float* pw_w; const float* pw_s; const float* pw_b;            // [16 ci][16 co]
-    float* out; int round_out;
+struct StemDs {                              // one or two backbones share a launch (blockIdx.z selects; both read the same image)
+    StemDsProblem q[2];
+    int round_out;
 };
 
 template <int STRIDE>
 __global__ void __launch_bounds__(256, 3)
-stem_ds_kernel(const float* __restrict__ img, int H, int W, int Hs, int Ws, int pad, StemDs p) {
+stem_ds_kernel(const float* __restrict__ img, int H, int W, int Hs, int Ws, int pad, const __grid_constant__ StemDs pp) {
+    struct { const float *stem_w, *stem_s, *stem_b, *dw_w, *dw_s, *dw_b, *pw_w, *pw_s, *pw_b; float* out; int round_out; } p;
+    {
+        const StemDsProblem& q = pp.q[blockIdx.z];
+        p.stem_w = q.stem_w; p.stem_s = q.stem_s; p.stem_b = q.stem_b; p.dw_w = q.dw_w; p.dw_s = q.dw_s; p.dw_b = q.dw_b;
+        p.pw_w = q.pw_w; p.pw_s = q.pw_s; p.pw_b = q.pw_b; p.out = q.out; p.round_out = pp.round_out;
+    }
     constexpr int PADO = STRIDE == 1 ? 1 : 0;              // depthwise TF-SAME pad_begin on an even-sized map
     constexpr int TO = SD_T / STRIDE;                      // output tile edge
     __shared__ __align__(16) float sP[3 * SD_PR * 2 * SD_PP];          // image patch [c][row][parity][col/2]; later D [256][16]
@@ -657,22 +707,28 @@ stem_ds_kernel(const float* __restrict__ img, int H, int W, int Hs, int Ws, int 
 }
 }  // namespace
 
-int stem_ds(const float* img, int B, int H, int W, const float* stem_w, const float* stem_s, const float* stem_b,
-            const float* dw_w, const float* dw_s, const float* dw_b, const float* pw_w, const float* pw_s, const float* pw_b,
-            int stride, int round_out, float* out, cudaStream_t st) {
+int stem_ds(const float* img, int B, int H, int W, const StemDsProblem* probs, int n, int stride, int round_out, cudaStream_t st) {
     const int Hs = (H + 1) / 2, Ws = (W + 1) / 2;
+    SMK_REQUIRE(n == 1 || n == 2, "stem_ds: one or two backbones per launch");
     SMK_REQUIRE(stride == 1 || stride == 2, "stem_ds: stride must be 1 or 2");
     SMK_REQUIRE(H % 2 == 0 && W % 2 == 0 && Hs % SD_T == 0 && Ws % SD_T == 0, "stem_ds: image size %dx%d must be a multiple of 32", H, W);
     SMK_REQUIRE(((uintptr_t)img & 7) == 0, "stem_ds: image pointer must be 8-byte aligned");
-    StemDs p{stem_w, stem_s, stem_b, dw_w, dw_s, dw_b, pw_w, pw_s, pw_b, out, round_out};
+    StemDs p{};
+    p.q[0] = probs[0]; p.q[1] = probs[n - 1]; p.round_out = round_out;
     const double px_o = (double)B * (Hs / stride) * (Ws / stride);
-    SMK_TAG("stem_ds_fused", 4.0 * ((double)B * 3 * H * W + px_o * 16 + 27 * 16 + 9 * 16 + 256 + 96),
-            2.0 * ((double)B * Hs * Ws * 16 * 27 + px_o * 16 * (9 + 16)), st);
-    dim3 grid((Hs / SD_T) * (Ws / SD_T), B);
+    SMK_TAG("stem_ds_fused", 4.0 * ((double)B * 3 * H * W + n * (px_o * 16 + 27 * 16 + 9 * 16 + 256 + 96)),
+            n * 2.0 * ((double)B * Hs * Ws * 16 * 27 + px_o * 16 * (9 + 16)), st);
+    dim3 grid((Hs / SD_T) * (Ws / SD_T), B, n);
     if (stride == 1) SMK_LAUNCH((stem_ds_kernel<1>), grid, dim3(256), 0, st, img, H, W, Hs, Ws, same_pad_begin(H, 2), p);
     else SMK_LAUNCH((stem_ds_kernel<2>), grid, dim3(256), 0, st, img, H, W, Hs, Ws, same_pad_begin(H, 2), p);
     SMK_CHECK_LAUNCH();
     return 0;
+}
+int stem_ds(const float* img, int B, int H, int W, const float* stem_w, const float* stem_s, const float* stem_b,
+            const float* dw_w, const float* dw_s, const float* dw_b, const float* pw_w, const float* pw_s, const float* pw_b,
+            int stride, int round_out, float* out, cudaStream_t st) {
+    StemDsProblem q{stem_w, stem_s, stem_b, dw_w, dw_s, dw_b, pw_w, pw_s, pw_b, out};
+    return stem_ds(img, B, H, W, &q, 1, stride, round_out, st);
 }
 
 int maxpool2x2(const float* in, int ld_in, int B, int H, int W, int C, float* out, cudaStream_t st) {
@@ -709,6 +765,24 @@ int gap_linear(const float* feat, int B, int HW, int C, const float* w, const fl
     SMK_CHECK_LAUNCH();
     SMK_TAG("head_linear", 4.0 * ((double)B * C + (double)n_out * C + (double)B * n_out), 2.0 * (double)B * C * n_out, st);
     SMK_LAUNCH(head_linear_kernel, dim3(dim3(B, cdiv(n_out, 8))), dim3(256), 0, st, pooled_scratch, C, w, bias, n_out, codes, out);
+    SMK_CHECK_LAUNCH();
+    return 0;
+}
+
+int gap_head(const GapHeadProblem* probs, int n, int B, int HW, int C, cudaStream_t st) {
+    SMK_REQUIRE(n == 1 || n == 2, "gap_head: one or two backbones per launch");
+    SMK_REQUIRE((size_t)C * 4 <= 48 * 1024, "gap_head: feature width too large for the shared-memory pool");
+    GapHead g{};
+    int max_out = 0;
+    for (int k = 0; k < 2; ++k) {
+        const GapHeadProblem& q = probs[k < n ? k : n - 1];
+        g.feat[k] = q.feat; g.w[k] = q.w; g.bias[k] = q.bias; g.codes[k] = q.codes; g.out[k] = q.out; g.n_out[k] = q.n_out;
+        max_out = std::max(max_out, q.n_out);
+    }
+    double by = 0, fl = 0;
+    for (int k = 0; k < n; ++k) { by += 4.0 * ((double)B * HW * C + (double)probs[k].n_out * C + (double)B * probs[k].n_out); fl += (double)B * C * HW + 2.0 * B * C * probs[k].n_out; }
+    SMK_TAG("gap_head", by, fl, st);
+    SMK_LAUNCH(gap_head_kernel, dim3(B, cdiv(max_out, 32), n), dim3(256), (size_t)C * 4, st, g, HW, C);
     SMK_CHECK_LAUNCH();
     return 0;
 }

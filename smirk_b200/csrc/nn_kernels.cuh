@@ -40,6 +40,14 @@ int stem_conv3(const float* img_nchw, int B, int H, int W, const float* const w[
                const float* const bias[3], float* const out[3], cudaStream_t st);
 // Fused stem (3x3 s2, 3 -> 16, BN, ReLU) + depthwise-separable block 0 (dw 3x3 s{1,2} + BN + ReLU, 1x1 16 -> 16 + BN,
 // + skip when stride 1) of one backbone: image NCHW fp32 -> [B, 112/stride, 112/stride, 16] NHWC.  pw_w is [ci][co] fp32.
+struct StemDsProblem {
+    const float* stem_w; const float* stem_s; const float* stem_b;      // [27][16], [16], [16]
+    const float* dw_w; const float* dw_s; const float* dw_b;            // [9][16]
+    const float* pw_w; const float* pw_s; const float* pw_b;            // [16 ci][16 co]
+    float* out;
+};
+// n = 1 or 2 backbones of the same block-0 stride in one launch (they read the same image).
+int stem_ds(const float* img_nchw, int B, int H, int W, const StemDsProblem* probs, int n, int stride, int round_out, cudaStream_t st);
 int stem_ds(const float* img_nchw, int B, int H, int W, const float* stem_w /*[27][16]*/, const float* stem_s, const float* stem_b,
             const float* dw_w /*[9][16]*/, const float* dw_s, const float* dw_b, const float* pw_w /*[16][16]*/, const float* pw_s,
             const float* pw_b, int stride, int round_out, float* out, cudaStream_t st);
@@ -53,5 +61,9 @@ int conv1x1_sigmoid_nchw(const float* in, int B, int HW, int Cin, const float* w
 //   0 none, 1 clamp[0,1], 2 relu, 3 clamp[-0.2,0.2]
 int gap_linear(const float* feat, int B, int HW, int C, const float* w /*[n_out][C]*/, const float* bias, int n_out,
                const uint8_t* clamp_codes /*device, may be null*/, float* pooled_scratch /*[B][C]*/, float* out, cudaStream_t st);
+
+// The same in one launch, for one or two backbones with the same feature shape [B, HW, C] (different head widths allowed).
+struct GapHeadProblem { const float* feat; const float* w; const float* bias; const uint8_t* codes; float* out; int n_out; };
+int gap_head(const GapHeadProblem* probs, int n, int B, int HW, int C, cudaStream_t st);
 
 }  // namespace smk

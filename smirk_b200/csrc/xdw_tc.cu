@@ -51,17 +51,19 @@ using namespace ptx;                            // PTX wrappers shared by the tc
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) { return make_idesc_tf32(M, N); }
 __device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+struct XdwMaps { CUtensorMap x[2], w[2], wlo[2]; };      // per problem: activations, 1x1 weights (TF32 heads), weight tails
+
 struct XdwArgs {
     int H, W, Ho, Wo;              // e (= x) resolution and output resolution
     int mid, nkb, nchunks;         // expanded channels, 32-wide k-blocks of Cin, 32-wide channel chunks
     int groups, chunks_per_group;  // a group owns chunks [g*cpg, min((g+1)*cpg, nchunks)); item = ((img*tiles_y + ty)*tiles_x + tx)*groups + g
-    int n_items;
+    int n_items, n_items_p;        // n_items_p: items per problem (two identically shaped problems may share one launch, like gemm_tc.cu)
     int pad;                       // TF-SAME pad_begin of the depthwise conv (1 for stride 1, 0 for stride 2 on even sizes)
     int tiles_x, tiles_y;          // output tiles per image
-    const float* scale1; const float* bias1;        // folded BN of the 1x1 conv        [mid]
-    const float* wdw;                               // depthwise weights                 [9][mid]
-    const float* scale2; const float* bias2;        // folded BN of the depthwise conv   [mid]
-    float* out;                                     // d: [B, Ho, Wo, mid]
+    const float* scale1[2]; const float* bias1[2];  // folded BN of the 1x1 conv        [mid]   (per problem)
+    const float* wdw[2];                            // depthwise weights                 [9][mid]
+    const float* scale2[2]; const float* bias2[2];  // folded BN of the depthwise conv   [mid]
+    float* out[2];                                  // d: [B, Ho, Wo, mid]
     int round_out;
 };
 
@@ -73,8 +75,7 @@ struct XdwArgs {
 // tails, so the SM keeps room for the other kernels of the concurrent pipeline.
 template <int STRIDE, int X3>
 __global__ void __launch_bounds__(NUM_THREADS + (X3 ? NUM_SPLITTERS : 0), X3 ? 1 : 2)
-xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
-           const XdwArgs a) {
+xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
     constexpr int TO = STRIDE == 1 ? 14 : 7;                    // output tile edge
     constexpr int STAGE_BYTES = X3 == 1 ? 2 * smk::STAGE_BYTES : (X3 == 2 ? smk::STAGE_BYTES + B_BYTES : smk::STAGE_BYTES);
     constexpr int LO = smk::STAGE_BYTES;                        // X3 == 1: offset of the tails ([x half 0][x half 1][w] again) within a stage
@@ -101,9 +102,10 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     // All three roles walk the same item sequence; the smem ring and the TMEM double buffer run across
     // item boundaries, so the x window / weights of item i+1 are in flight (and multiplied) while the
     // workers are still busy with item i.
-    struct Item { int img, oh0, ow0, c_begin, c_end; };
+    struct Item { int prob, img, oh0, ow0, c_begin, c_end; };
     auto decode = [&](int item) {
         Item w;
+        w.prob = item >= a.n_items_p ? 1 : 0; item -= w.prob * a.n_items_p;
         const int grp = item % a.groups; int r = item / a.groups;
         const int tx = r % a.tiles_x; r /= a.tiles_x;
         const int ty = r % a.tiles_y; w.img = r / a.tiles_y;
@@ -113,9 +115,9 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     };
 
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-        if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWlo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mp.x[0]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mp.w[0]) : "memory");
+        if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&mp.wlo[0]) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&split[s], NUM_SPLITTERS / 32); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NUM_WORKERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -143,10 +145,10 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                         mbar_wait(&empty[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
                         uint8_t* st = smem + s * STAGE_BYTES;
                         mbar_expect_tx(&full[s], (uint32_t)(smk::STAGE_BYTES + (X3 ? B_BYTES : 0)));
-                        tma_load_4d(&tmX, st, &full[s], kb * BK, ex0, ey0, w.img);
-                        tma_load_4d(&tmX, st + HALF_BYTES, &full[s], kb * BK, ex0, ey0 + 8, w.img);
-                        tma_load_2d(&tmW, st + 2 * HALF_BYTES, &full[s], kb * BK, c * NC);
-                        if (X3) tma_load_2d(&tmWlo, st + WLO, &full[s], kb * BK, c * NC);
+                        tma_load_4d(&mp.x[w.prob], st, &full[s], kb * BK, ex0, ey0, w.img);
+                        tma_load_4d(&mp.x[w.prob], st + HALF_BYTES, &full[s], kb * BK, ex0, ey0 + 8, w.img);
+                        tma_load_2d(&mp.w[w.prob], st + 2 * HALF_BYTES, &full[s], kb * BK, c * NC);
+                        if (X3) tma_load_2d(&mp.wlo[w.prob], st + WLO, &full[s], kb * BK, c * NC);
                     }
             }
         }
@@ -244,20 +246,23 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         // it for chunk i+1 before it starts waiting for the accumulator of chunk i and parks it after phase (a) —
         // the global-load latency is off the critical path and phases (a)/(b) read parameters with LDS.
         const int prow = t >> 4, pcol = (t & 15) * 2;
-        const float* psrc = nullptr;
-        if (t < PAR_ROWS * 16) {
-            psrc = prow == 0 ? a.scale1 : prow == 1 ? a.bias1 : prow == 11 ? a.scale2 : prow == 12 ? a.bias2 : a.wdw + (size_t)(prow - 2) * a.mid;
-            psrc += pcol;
+        const bool par_owner = t < PAR_ROWS * 16;
+        const float* psrc[2] = {nullptr, nullptr};
+        if (par_owner) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+                psrc[q] = (prow == 0 ? a.scale1[q] : prow == 1 ? a.bias1[q] : prow == 11 ? a.scale2[q] : prow == 12 ? a.bias2[q]
+                                                                                       : a.wdw[q] + (size_t)(prow - 2) * a.mid) + pcol;
         }
-        auto load_par = [&](int c) {
+        auto load_par = [&](int prob, int c) {
             float2 v = make_float2(0.f, 0.f);
-            if (psrc && c * NC + pcol < a.mid) v = __ldg(reinterpret_cast<const float2*>(psrc + c * NC));
+            if (par_owner && c * NC + pcol < a.mid) v = __ldg(reinterpret_cast<const float2*>(psrc[prob] + c * NC));
             return v;
         };
         auto park_par = [&](int slot_idx, const float2& v) {
-            if (psrc) *reinterpret_cast<float2*>(PAR + slot_idx * (PAR_ROWS * NC) + prow * NC + pcol) = v;
+            if (par_owner) *reinterpret_cast<float2*>(PAR + slot_idx * (PAR_ROWS * NC) + prow * NC + pcol) = v;
         };
-        if ((int)blockIdx.x < a.n_items) park_par(0, load_par(decode(blockIdx.x).c_begin));
+        if ((int)blockIdx.x < a.n_items) { const Item w0 = decode(blockIdx.x); park_par(0, load_par(w0.prob, w0.c_begin)); }
         worker_barrier();
         int cc = 0;
         for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
@@ -270,15 +275,15 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           const int n_rg = min(32 / ncols, nrows), rpt = (nrows + n_rg - 1) / n_rg;
           const int dw_ox = slot % ncols, dw_rg = slot / ncols;
           const int dw_oy0 = dw_rg * rpt, dw_oy1 = dw_rg < n_rg ? min(nrows, dw_oy0 + rpt) : 0;
-          int next_first = -1;                             // first chunk of this CTA's next item (-1: none)
-          if (item + (int)gridDim.x < a.n_items) next_first = decode(item + gridDim.x).c_begin;
+          int next_first = -1, next_prob = 0;              // first chunk (and problem) of this CTA's next item (-1: none)
+          if (item + (int)gridDim.x < a.n_items) { const Item wn = decode(item + gridDim.x); next_first = wn.c_begin; next_prob = wn.prob; }
           for (int c = w.c_begin; c < w.c_end; ++c, ++cc) {
             const int buf = cc & 1;
             const int ch0 = c * NC;
             const float* par = PAR + buf * (PAR_ROWS * NC);
             const int c_next = c + 1 < w.c_end ? c + 1 : next_first;
             float2 pf = make_float2(0.f, 0.f);
-            if (c_next >= 0) pf = load_par(c_next);
+            if (c_next >= 0) pf = load_par(c + 1 < w.c_end ? w.prob : next_prob, c_next);
             mbar_wait(&acc_full[buf], (uint32_t)(cc >> 1) & 1u);
             tcgen05_fence_after();
             // (a) TMEM -> BN1 + ReLU -> E   (rows = window pixels, lane = pixel).  Channels past `mid` have zero
@@ -326,7 +331,7 @@ xdw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                 for (int q = 0; q < 9; ++q) k[q] = *reinterpret_cast<const float4*>(par + (2 + q) * NC + cq * 4);
                 const float4 s2 = *reinterpret_cast<const float4*>(par + 11 * NC + cq * 4);
                 const float4 b2 = *reinterpret_cast<const float4*>(par + 12 * NC + cq * 4);
-                float* orow = a.out + (((size_t)img * a.Ho + oh0 + dw_oy0) * a.Wo + ow0 + dw_ox) * a.mid + ch;
+                float* orow = a.out[w.prob] + (((size_t)img * a.Ho + oh0 + dw_oy0) * a.Wo + ow0 + dw_ox) * a.mid + ch;
                 const size_t orow_stride = (size_t)a.Wo * a.mid;
                 auto emit = [&](const float4& acc) {
                     float4 o = fma4(acc, s2, b2);
@@ -400,52 +405,63 @@ int load_encoder() {
 
 }  // namespace
 
-int xdw_conv(const XdwConv& p, cudaStream_t st) {
+int xdw_conv(const XdwConv& p, cudaStream_t st, const XdwConv* p2) {
     if (int rc = load_encoder()) return rc;
+    const int nprob = p2 ? 2 : 1;
     SMK_REQUIRE(p.stride == 1 || p.stride == 2, "xdw_conv: stride must be 1 or 2");
     SMK_REQUIRE(p.Cin % 4 == 0 && p.mid % 4 == 0, "xdw_conv: Cin and mid must be multiples of 4");
     SMK_REQUIRE(p.stride == 1 || (p.H % 2 == 0 && p.W % 2 == 0), "xdw_conv: stride 2 expects even input sizes (TF-SAME pad_begin 0)");
+    SMK_REQUIRE(!p2 || (p2->B == p.B && p2->H == p.H && p2->W == p.W && p2->Cin == p.Cin && p2->mid == p.mid && p2->stride == p.stride &&
+                        p2->round_out == p.round_out && !p2->w1t_lo == !p.w1t_lo), "xdw_conv: paired problems must have identical shapes");
     const int Ho = (p.H + p.stride - 1) / p.stride, Wo = (p.W + p.stride - 1) / p.stride;
     const int TO = p.stride == 1 ? 14 : 7;
-    CUtensorMap tmX, tmW, tmWlo;
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
-        cuuint64_t strides[3] = {(cuuint64_t)p.Cin * 4, (cuuint64_t)p.W * p.Cin * 4, (cuuint64_t)p.H * p.W * p.Cin * 4};
-        cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)WIN, 8, 1};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = g_encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p.x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        SMK_REQUIRE(r == CUDA_SUCCESS, "xdw_conv: cuTensorMapEncodeTiled(x) failed (%d): B=%d H=%d W=%d Cin=%d", (int)r, p.B, p.H, p.W, p.Cin);
-    }
-    {
-        cuuint64_t dims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)p.mid};
-        cuuint64_t strides[1] = {(cuuint64_t)p.Cin * 4};
-        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)NC};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = g_encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p.w1t, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        SMK_REQUIRE(r == CUDA_SUCCESS, "xdw_conv: cuTensorMapEncodeTiled(w1) failed (%d): mid=%d Cin=%d", (int)r, p.mid, p.Cin);
-        tmWlo = tmW;
-        if (p.w1t_lo) {
-            r = g_encode(&tmWlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p.w1t_lo, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            SMK_REQUIRE(r == CUDA_SUCCESS, "xdw_conv: cuTensorMapEncodeTiled(w1 tails) failed (%d)", (int)r);
+    XdwMaps mp;
+    XdwArgs a{};
+    for (int g = 0; g < nprob; ++g) {
+        const XdwConv& q = g ? *p2 : p;
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)q.Cin, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.B};
+            cuuint64_t strides[3] = {(cuuint64_t)q.Cin * 4, (cuuint64_t)q.W * q.Cin * 4, (cuuint64_t)q.H * q.W * q.Cin * 4};
+            cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)WIN, 8, 1};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult r = g_encode(&mp.x[g], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)q.x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            SMK_REQUIRE(r == CUDA_SUCCESS, "xdw_conv: cuTensorMapEncodeTiled(x) failed (%d): B=%d H=%d W=%d Cin=%d", (int)r, q.B, q.H, q.W, q.Cin);
         }
+        {
+            cuuint64_t dims[2] = {(cuuint64_t)q.Cin, (cuuint64_t)q.mid};
+            cuuint64_t strides[1] = {(cuuint64_t)q.Cin * 4};
+            cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)NC};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = g_encode(&mp.w[g], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)q.w1t, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            SMK_REQUIRE(r == CUDA_SUCCESS, "xdw_conv: cuTensorMapEncodeTiled(w1) failed (%d): mid=%d Cin=%d", (int)r, q.mid, q.Cin);
+            mp.wlo[g] = mp.w[g];
+            if (q.w1t_lo) {
+                r = g_encode(&mp.wlo[g], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)q.w1t_lo, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                SMK_REQUIRE(r == CUDA_SUCCESS, "xdw_conv: cuTensorMapEncodeTiled(w1 tails) failed (%d)", (int)r);
+            }
+        }
+        a.scale1[g] = q.scale1; a.bias1[g] = q.bias1; a.wdw[g] = q.wdw; a.scale2[g] = q.scale2; a.bias2[g] = q.bias2; a.out[g] = q.out;
+    }
+    if (nprob == 1) {
+        mp.x[1] = mp.x[0]; mp.w[1] = mp.w[0]; mp.wlo[1] = mp.wlo[0];
+        a.scale1[1] = a.scale1[0]; a.bias1[1] = a.bias1[0]; a.wdw[1] = a.wdw[0]; a.scale2[1] = a.scale2[0]; a.bias2[1] = a.bias2[0]; a.out[1] = a.out[0];
     }
     static const int slots_lo = []() { const char* e = getenv("SMK_XDW_SLOTS"); return e ? atoi(e) : 148; }();   // resident CTAs to aim for: one per SM leaves half of every SM to concurrent kernels (+4 % end to end vs 296)
     static const int slots_hi = []() { const char* e = getenv("SMK_XDW_SLOTS_HI"); return e ? atoi(e) : 0; }();  // layers with >= 296 output tiles (0: same as SMK_XDW_SLOTS)
-    const int slots = (slots_hi > 0 && (long)cdiv(Wo, TO) * cdiv(Ho, TO) * p.B >= 296) ? slots_hi : slots_lo;
-    XdwArgs a{};
+    const int slots = (slots_hi > 0 && (long)nprob * cdiv(Wo, TO) * cdiv(Ho, TO) * p.B >= 296) ? slots_hi : slots_lo;
     a.H = p.H; a.W = p.W; a.Ho = Ho; a.Wo = Wo; a.mid = p.mid; a.nkb = cdiv(p.Cin, BK); a.nchunks = cdiv(p.mid, NC);
-    {   // split the channel chunks over enough CTAs to fill 148 SMs x 2 CTAs
-        const long tiles = (long)cdiv(Wo, TO) * cdiv(Ho, TO) * p.B;
+    {   // split the channel chunks over enough CTAs to fill the resident slots
+        const long tiles = (long)nprob * cdiv(Wo, TO) * cdiv(Ho, TO) * p.B;
         int groups = (int)std::min<long>(a.nchunks, std::max<long>(1, (slots + tiles - 1) / tiles));
         a.chunks_per_group = cdiv(a.nchunks, groups);
         a.groups = cdiv(a.nchunks, a.chunks_per_group);
     }
     a.pad = p.stride == 1 ? 1 : 0;
     a.tiles_x = cdiv(Wo, TO); a.tiles_y = cdiv(Ho, TO);
-    a.scale1 = p.scale1; a.bias1 = p.bias1; a.wdw = p.wdw; a.scale2 = p.scale2; a.bias2 = p.bias2; a.out = p.out; a.round_out = p.round_out;
+    a.round_out = p.round_out;
     constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + E_BYTES + PAR_BYTES + 1024 + 256;
     constexpr size_t smem3 = (size_t)STAGES * 2 * STAGE_BYTES + E_BYTES + PAR_BYTES + 1024 + 256;          // tails in shared memory
     constexpr size_t smem3t = (size_t)STAGES * (STAGE_BYTES + B_BYTES) + E_BYTES + PAR_BYTES + 1024 + 256;  // tails in tensor memory
@@ -464,23 +480,24 @@ int xdw_conv(const XdwConv& p, cudaStream_t st) {
         if (dev < 64) configured_mask |= 1ull << dev;
     }
     {
-        const double px_in = (double)p.B * p.H * p.W, px_out = (double)p.B * Ho * Wo;
+        const double px_in = (double)nprob * p.B * p.H * p.W, px_out = (double)nprob * p.B * Ho * Wo;
         const char* tag = p.w1t_lo ? "xdw_fused_tc3x" : "xdw_fused_tc";
         if (g_prof_detail) tag = prof_shape_tag(tag, (long)px_out, p.Cin, p.mid);
-        SMK_TAG(tag, 4.0 * (px_in * p.Cin + px_out * p.mid + (double)p.mid * (p.Cin + 13)), 2.0 * px_in * p.Cin * p.mid + 18.0 * px_out * p.mid, st);
+        SMK_TAG(tag, 4.0 * (px_in * p.Cin + px_out * p.mid + (double)nprob * p.mid * (p.Cin + 13)), 2.0 * px_in * p.Cin * p.mid + 18.0 * px_out * p.mid, st);
     }
-    a.n_items = a.tiles_x * a.tiles_y * p.B * a.groups;
+    a.n_items_p = a.tiles_x * a.tiles_y * p.B * a.groups;
+    a.n_items = nprob * a.n_items_p;
     dim3 grid((unsigned)std::min(a.n_items, p.w1t_lo ? std::min(slots, 148) : slots));            // persistent: (up to) 2 CTAs per SM
     static const int x3_tmem = []() { const char* e = getenv("SMK_X3_TMEM"); return e ? atoi(e) : 1; }();
     if (p.w1t_lo && x3_tmem) {
-        if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, 2>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3t, st, tmX, tmW, tmWlo, a);
-        else SMK_LAUNCH((xdw_kernel<2, 2>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3t, st, tmX, tmW, tmWlo, a);
+        if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, 2>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3t, st, mp, a);
+        else SMK_LAUNCH((xdw_kernel<2, 2>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3t, st, mp, a);
     } else if (p.w1t_lo) {
-        if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, 1>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3, st, tmX, tmW, tmWlo, a);
-        else SMK_LAUNCH((xdw_kernel<2, 1>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3, st, tmX, tmW, tmWlo, a);
+        if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, 1>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3, st, mp, a);
+        else SMK_LAUNCH((xdw_kernel<2, 1>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3, st, mp, a);
     } else {
-        if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, 0>), dim3(grid), dim3(NUM_THREADS), smem, st, tmX, tmW, tmWlo, a);
-        else SMK_LAUNCH((xdw_kernel<2, 0>), dim3(grid), dim3(NUM_THREADS), smem, st, tmX, tmW, tmWlo, a);
+        if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, 0>), dim3(grid), dim3(NUM_THREADS), smem, st, mp, a);
+        else SMK_LAUNCH((xdw_kernel<2, 0>), dim3(grid), dim3(NUM_THREADS), smem, st, mp, a);
     }
     SMK_CHECK_LAUNCH();
     return 0;

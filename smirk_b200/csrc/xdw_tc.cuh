@@ -18,6 +18,7 @@ struct XdwConv {
     float* out;                           // d: [B,Ho,Wo,mid]
 };
 
-int xdw_conv(const XdwConv& p, cudaStream_t st);
+// p2 (optional): a second problem of identical shape sharing the launch.
+int xdw_conv(const XdwConv& p, cudaStream_t st, const XdwConv* p2 = nullptr);
 
 }  // namespace smk
