@@ -16,7 +16,11 @@ import json
 import re
 
 TAGS = [
-    (r"xdw_kernel", "xdw_fused_tc"), (r"gemm_tc_kernel", "pw_gemm_tc"), (r"conv3_sw_kernel", "conv3x3_sw_tc"),
+    (r"xdw_kernel<\d+, *[12]>", "xdw_fused_tc3x"), (r"xdw_kernel", "xdw_fused_tc"),
+    (r"gemm_tc_kernel<\d+, *\d+, *\d+, *(false|0), *[12]>", "pw_gemm_tc3x"),            # 3xTF32 variants (single-tile CTAs)
+    (r"gemm_tc_kernel<\d+, *\d+, *\d+, *(true|1), *0>", "conv3x3_gemm_tc"),             # persistent CTAs: the generator's 3x3 convolutions
+    (r"gemm_tc_kernel", "pw_gemm_tc"),                                                  # 1x1 convs / transposed convs
+    (r"gap_head_kernel", "gap_head"), (r"mask_\w+_kernel", "masking"),
     (r"stem_ds_kernel", "stem_ds_fused"), (r"stem_conv3_kernel", "stem_conv3"), (r"stem_conv_kernel", "stem_conv"),
     (r"dwconv3x3", "dwconv3x3"), (r"conv_gemm_kernel", "conv_gemm_f32"), (r"raster_tile_kernel", "raster_tile"),
     (r"flame_verts_kernel", "flame_verts"), (r"flame_pose_kernel", "flame_pose"), (r"flame_landmarks_kernel", "flame_landmarks"),
@@ -33,6 +37,7 @@ def main():
     ap.add_argument("out")
     ap.add_argument("--last-pass", type=int, default=0)
     ap.add_argument("--source", default="")
+    ap.add_argument("--passes", type=int, default=1, help="forward passes covered by the selected launches (step traffic = total / passes)")
     a = ap.parse_args()
     rows = [r for r in csv.reader(open(a.csv, errors="replace")) if len(r) > 10]
     hdr = next(r for r in rows if r[0] == "ID")
@@ -62,7 +67,10 @@ def main():
     tot = sum(o["ncu_us"] for o in out.values())
     for o in out.values():
         o["share_of_ncu_time"] = o["ncu_us"] / tot
-    json.dump({"source": a.source or ("ncu csv %s, last %d launches" % (a.csv, len(lib))), "kernels": out}, open(a.out, "w"), indent=1)
+    step = sum(o["dram_read_bytes"] + o["dram_write_bytes"] for o in out.values()) / max(1, a.passes)
+    json.dump({"source": a.source or ("ncu csv %s, last %d launches" % (a.csv, len(lib))), "launches": len(lib), "passes": a.passes,
+               "step_traffic_bytes": step, "kernels": out}, open(a.out, "w"), indent=1)
+    print("step DRAM traffic: %.1f MB over %d launches" % (step / 1e6, len(lib) // max(1, a.passes)))
     for t, o in sorted(out.items(), key=lambda kv: -kv[1]["ncu_us"]):
         print("%-18s x%-3d %9.1f us  share %.3f  dram/launch %8.2f MB" % (t, o["launches"], o["ncu_us"], o["share_of_ncu_time"], o["traffic_bytes_per_launch"] / 1e6))
 
