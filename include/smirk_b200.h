@@ -12,8 +12,11 @@
  *     (thread-local).  No exceptions, no exit().
  *   - `*_create` take HOST pointers to fp32 / int32 constant arrays, fold/pack them and upload to the
  *     CURRENT CUDA device; handles are immutable afterwards.  `*_forward` take DEVICE pointers
- *     (contiguous, 16-byte aligned), never allocate, never synchronise, and enqueue all work on the
- *     caller's stream (cudaStream_t passed as void*) — CUDA-graph capturable.
+ *     (contiguous, 16-byte aligned), never allocate, never synchronise, and order all work after / before
+ *     the caller's stream (cudaStream_t passed as void*) — CUDA-graph capturable.  smk_encoder_forward
+ *     runs its backbones as parallel branches that fork from and join back into that stream, using
+ *     per-call fork/join events and side streams taken round-robin from a pool of 8 inside the handle:
+ *     forwards are re-entrant (up to 8 in flight per encoder handle) given distinct workspaces.
  *   - the caller owns inputs, outputs and the workspace (size from `*_workspace_bytes`).
  */
 #ifndef SMIRK_B200_H
@@ -189,9 +192,14 @@ int smk_masking_face_weights(const SmkMasking* h, const float* trans_verts, cons
                              float* weights, void* ws, size_t ws_bytes, void* stream);
 int smk_masking_points(const SmkMasking* h, const float* trans_verts, const int64_t* face_idx, const float* bary,
                        int B, int N, int image_size, int64_t* npoints, void* stream);
+/* extra_points [B,3,S,S] (nullable): masking()'s third argument given explicitly (masking.py:71; the trainer passes the
+ * result of transfer_pixels) instead of img * point-mask(npoints, rbound).                                                 */
 int smk_masking_compose(const SmkMasking* h, const float* img, const float* hull, const int64_t* npoints, const int64_t* rbound,
-                        int N, const float* rendered_mask, const float* noise_mult, const float* random_centres,
+                        int N, const float* extra_points, const float* rendered_mask, const float* noise_mult, const float* random_centres,
                         int wr, int B, int S, float* masked, void* ws, size_t ws_bytes, void* stream);
+/* transfer_pixels (masking.py:116-129): points int64 [B,N,2] (x, y); rbound int64 [B] or NULL; ws >= B*S*S*4 bytes.       */
+int smk_masking_transfer_pixels(const float* img, const int64_t* points1, const int64_t* points2, const int64_t* rbound,
+                                int B, int N, int S, float* out, void* ws, size_t ws_bytes, void* stream);
 /* The whole step of demo.py:138-165 with the random draws made on the device (Philox4x32-10, keyed by rng_state[0] = seed
  * and rng_state[1] = call counter, which the call increments on the stream — graph replays draw fresh samples):
  *   face weights -> N = int(mask_ratio * ratio_mul * S * S) faces by inverse CDF (multinomial with replacement) -> uniform

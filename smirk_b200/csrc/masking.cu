@@ -138,8 +138,8 @@ mask_hmax_kernel(const float* __restrict__ hull, const float* __restrict__ centr
 // vertical halves + composite (masking.py:79-100)
 __global__ void __launch_bounds__(256)
 mask_compose_kernel(const float* __restrict__ img, const float* __restrict__ th, const float* __restrict__ tc,
-                    const uint8_t* __restrict__ pm, const float* __restrict__ rendered_mask, const float* __restrict__ noise_mult,
-                    int B, int S, int wr, float* __restrict__ out) {
+                    const uint8_t* __restrict__ pm, const float* __restrict__ extra, const float* __restrict__ rendered_mask,
+                    const float* __restrict__ noise_mult, int B, int S, int wr, float* __restrict__ out) {
     smk::pdl_sync();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)B * S * S) return;
@@ -157,12 +157,12 @@ mask_compose_kernel(const float* __restrict__ img, const float* __restrict__ th,
         for (int dy = -5; dy <= 5; ++dy) { const int yy = y + dy; if (yy >= 0 && yy < S) c = fmaxf(c, ccol[(size_t)yy * S]); }
         keep = __fsub_rn(1.0f, c);
     }
-    const float on = pm[i] ? 1.0f : 0.0f;
+    const float on = (pm && pm[i]) ? 1.0f : 0.0f;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         const size_t o = ((size_t)b * 3 + ch) * S * S + pix;
         const float v = img[o];
-        float e = __fmul_rn(v, on);                                   // extra_points = img * pmask
+        float e = extra ? extra[o] : __fmul_rn(v, on);                // extra_points: given (masking.py:71), or img * pmask (demo.py:162)
         if (noise_mult) e = __fmul_rn(e, noise_mult[o]);
         if (tc) e = __fmul_rn(e, keep);
         out[o] = e > 0.0f ? e : __fmul_rn(v, mask);
@@ -268,6 +268,37 @@ mask_rendered_kernel(const float* __restrict__ rendered, int B, int S, float* __
 
 __global__ void mask_rng_advance_kernel(uint64_t* rng) { smk::pdl_sync(); if (threadIdx.x == 0) rng[1] += 1; }
 
+// transfer_pixels (masking.py:116-129): out[b, :, p2.y, p2.x] = img[b, :, p1.y, p1.x] for the first rbound[b] (or all) point
+// pairs; with duplicate targets the LAST pair in index order wins (the sequential semantics of the reference's indexed
+// assignment).  Pass 1: winner[target pixel] = max pair index (atomicMax); pass 2: every pixel copies from its winner.
+__global__ void __launch_bounds__(256)
+mask_transfer_winner_kernel(const int64_t* __restrict__ p2, const int64_t* __restrict__ rbound, int B, int N, int S, int* __restrict__ winner) {
+    smk::pdl_sync();
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)B * N) return;
+    const int b = (int)(i / N), j = (int)(i - (long)b * N);
+    if (rbound && j >= rbound[b]) return;
+    const int64_t x = p2[i * 2], y = p2[i * 2 + 1];
+    if (x < 0 || x >= S || y < 0 || y >= S) return;
+    atomicMax(winner + ((size_t)b * S + y) * S + x, j);
+}
+__global__ void __launch_bounds__(256)
+mask_transfer_copy_kernel(const float* __restrict__ img, const int64_t* __restrict__ p1, const int* __restrict__ winner, int B, int N, int S,
+                          float* __restrict__ out) {
+    smk::pdl_sync();
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)B * S * S) return;
+    const int b = (int)(i / ((long)S * S)); const long pix = i - (long)b * S * S;
+    const int j = winner[i];
+    int64_t sx = 0, sy = 0;
+    if (j >= 0) { sx = p1[((size_t)b * N + j) * 2]; sy = p1[((size_t)b * N + j) * 2 + 1]; }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const size_t o = ((size_t)b * 3 + ch) * S * S;
+        out[o + pix] = j >= 0 ? img[o + (size_t)sy * S + sx] : 0.f;
+    }
+}
+
 }  // namespace
 
 struct SmkMasking {
@@ -333,11 +364,31 @@ extern "C" int smk_masking_points(const SmkMasking* h, const float* trans_verts,
     return 0;
 }
 
+extern "C" int smk_masking_transfer_pixels(const float* img, const int64_t* points1, const int64_t* points2, const int64_t* rbound,
+                                           int B, int N, int S, float* out, void* ws, size_t ws_bytes, void* stream) {
+    if (B == 0) return 0;
+    SMK_REQUIRE(img && out && (N == 0 || (points1 && points2)) && S > 0, "smk_masking_transfer_pixels: bad argument");
+    SMK_REQUIRE(ws && ws_bytes >= (size_t)B * S * S * sizeof(int), "smk_masking_transfer_pixels: workspace too small (B*S*S ints)");
+    cudaStream_t st = (cudaStream_t)stream;
+    int* winner = reinterpret_cast<int*>(ws);
+    SMK_CHECK_CUDA(cudaMemsetAsync(winner, 0xFF, (size_t)B * S * S * sizeof(int), st));        // -1
+    if (N > 0) {
+        SMK_TAG("mask_transfer_winner", 20.0 * B * N, 0.0, st);
+        SMK_LAUNCH(mask_transfer_winner_kernel, dim3(smk::cdiv((long)B * N, 256)), dim3(256), 0, st, points2, rbound, B, N, S, winner);
+        SMK_CHECK_LAUNCH();
+    }
+    SMK_TAG("mask_transfer_copy", 4.0 * B * S * S * 5.0, 0.0, st);
+    SMK_LAUNCH(mask_transfer_copy_kernel, dim3(smk::cdiv((long)B * S * S, 256)), dim3(256), 0, st, img, points1, (const int*)winner, B, N, S, out);
+    SMK_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int smk_masking_compose(const SmkMasking* h, const float* img, const float* hull, const int64_t* npoints, const int64_t* rbound,
-                                   int N, const float* rendered_mask, const float* noise_mult, const float* random_centres,
+                                   int N, const float* extra_points, const float* rendered_mask, const float* noise_mult, const float* random_centres,
                                    int wr, int B, int S, float* masked, void* ws, size_t ws_bytes, void* stream) {
     if (B == 0) return 0;
-    SMK_REQUIRE(h && img && hull && masked && (N == 0 || (npoints && rbound)) && wr >= 0 && S > 0, "smk_masking_compose: bad argument");
+    SMK_REQUIRE(h && img && hull && masked && (N == 0 || extra_points || (npoints && rbound)) && wr >= 0 && S > 0, "smk_masking_compose: bad argument");
+    if (extra_points) N = 0;                            // the caller supplies extra_points (masking.py:71); no point mask to build
     SMK_REQUIRE(ws && ws_bytes >= smk_masking_workspace_bytes(h, B, S), "smk_masking_compose: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     smk::Workspace w(ws, ws_bytes);
@@ -358,7 +409,7 @@ extern "C" int smk_masking_compose(const SmkMasking* h, const float* img, const 
     SMK_CHECK_LAUNCH();
     SMK_TAG("mask_compose", 4.0 * npx * (3 + 3 + 2 + (noise_mult ? 3 : 0)), 0.0, st);
     SMK_LAUNCH(mask_compose_kernel, dim3(smk::cdiv(npx, 256)), dim3(256), 0, st, img, (const float*)th, (const float*)(random_centres ? tc : nullptr),
-               (const uint8_t*)pm, rendered_mask, noise_mult, B, S, wr, masked);
+               (const uint8_t*)pm, extra_points, rendered_mask, noise_mult, B, S, wr, masked);
     SMK_CHECK_LAUNCH();
     return 0;
 }
@@ -413,7 +464,7 @@ extern "C" int smk_masking_forward(const SmkMasking* h, const float* img, const 
     SMK_TAG("mask_rendered", 16.0 * npx, 0.0, st);
     SMK_LAUNCH(mask_rendered_kernel, dim3(smk::cdiv(npx, 256)), dim3(256), 0, st, rendered, B, S, rmask);
     SMK_CHECK_LAUNCH();
-    if (int rc = smk_masking_compose(h, img, hull, npoints, rbound, N, rmask, extra_noise ? noise : nullptr, p_centre > 0.f ? centres : nullptr,
+    if (int rc = smk_masking_compose(h, img, hull, npoints, rbound, N, nullptr, rmask, extra_noise ? noise : nullptr, p_centre > 0.f ? centres : nullptr,
                                      wr, B, S, masked, ws, base, stream)) return rc;
     SMK_TAG("mask_rng_advance", 16.0, 0.0, st);
     SMK_LAUNCH(mask_rng_advance_kernel, dim3(1), dim3(32), 0, st, rng_state);

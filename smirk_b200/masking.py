@@ -106,9 +106,50 @@ def masking_from_points(img, mask, npoints, rbound, wr=15, rendered_mask=None, n
     rb = rbound.to(img.device, torch.int64).contiguous()
     ws, n = ctx.workspace(B, S, img.device)
     ptr = lambda t: 0 if t is None else t.data_ptr()
-    _lib.check(_lib.lib().smk_masking_compose(ctx._h, img.data_ptr(), ptr(keep[0]), npts.data_ptr(), rb.data_ptr(), npts.shape[1],
+    _lib.check(_lib.lib().smk_masking_compose(ctx._h, img.data_ptr(), ptr(keep[0]), npts.data_ptr(), rb.data_ptr(), npts.shape[1], 0,
                                               ptr(keep[1]), ptr(keep[2]), ptr(keep[3]), int(wr), B, S, out.data_ptr(),
                                               ws.data_ptr(), n, _lib.stream_ptr(img.device)), "smk_masking_compose")
+    return out
+
+
+def transfer_pixels(img, points1, points2, rbound=None):
+    """masking.py:116-129 — same arguments and result.  With duplicate targets the last pair in index order wins."""
+    _lib.require_cuda(img, "img")
+    img = img.float().contiguous()
+    B, _, S, _ = img.shape
+    p1 = points1[..., :2].to(img.device, torch.int64).contiguous()
+    p2 = points2[..., :2].to(img.device, torch.int64).contiguous()
+    rb = rbound.to(img.device, torch.int64).contiguous() if rbound is not None else None
+    out = torch.empty_like(img)
+    if B == 0:
+        return out
+    ws = torch.empty(B * S * S, dtype=torch.int32, device=img.device)
+    with torch.cuda.device(img.device):
+        _lib.check(_lib.lib().smk_masking_transfer_pixels(img.data_ptr(), p1.data_ptr(), p2.data_ptr(), rb.data_ptr() if rb is not None else 0,
+                                                          B, p1.shape[1], S, out.data_ptr(), ws.data_ptr(), ws.numel() * 4,
+                                                          _lib.stream_ptr(img.device)), "smk_masking_transfer_pixels")
+    return out
+
+
+def masking(img, mask, extra_points, wr=15, rendered_mask=None, extra_noise=True, random_mask=0.01, flame_faces=None, n_verts=5023):
+    """masking.py:71-102 — same arguments and result; the two random draws are made with torch on the image's device
+    (as the reference does), the dilation / composite runs in ``csrc/masking.cu``."""
+    _lib.require_cuda(img, "img")
+    img = img.float().contiguous()
+    B, _, S, _ = img.shape
+    ctx = _context(flame_faces, n_verts) if flame_faces is not None else (next(iter(_CTX.values())) if _CTX else MaskingContext(torch.tensor([[0, 1, 2]]), 3))
+    noise = (torch.randn_like(img) * 0.05 + 1) if extra_noise else None
+    centres = torch.bernoulli(torch.ones((B, 1, S, S), device=img.device) * random_mask) if random_mask > 0 else None
+    f = lambda t: None if t is None else t.to(img.device, torch.float32).contiguous()
+    hull, extra, rmask = f(mask), f(extra_points), f(rendered_mask)
+    out = torch.empty_like(img)
+    if B == 0:
+        return out
+    ptr = lambda t: 0 if t is None else t.data_ptr()
+    with torch.cuda.device(img.device):
+        ws, n = ctx.workspace(B, S, img.device)
+        _lib.check(_lib.lib().smk_masking_compose(ctx._h, img.data_ptr(), hull.data_ptr(), 0, 0, 0, extra.data_ptr(), ptr(rmask), ptr(noise), ptr(centres),
+                                                  int(wr), B, S, out.data_ptr(), ws.data_ptr(), n, _lib.stream_ptr(img.device)), "smk_masking_compose")
     return out
 
 

@@ -136,3 +136,37 @@ def test_masking_stage_sampling_follows_the_face_weights(native_lib, g, faces):
     st.reseed(4242, 0)
     out2, d2 = st.forward(img, hull, tv.to(DEV), rend, debug=True)
     assert torch.equal(out2, first[0]) and torch.equal(d2["sampled_faces_indices"].cpu()[0], first[1])
+
+
+# ------------------------------------------------------------------------------ transfer_pixels / masking() with the reference's signatures
+def test_transfer_pixels_matches_reference(native_lib, g, faces):
+    """masking.py:116-129 incl. duplicate targets (last pair in index order wins) and the rbound variant, against the
+    outputs of the reference's own function stored in the golden file."""
+    from smirk_b200 import masking
+    img = synth_inputs.images(2, int(g["seeds"][2])).to(DEV)
+    p1, p2 = T(g["p1"], torch.long), T(g["p2"], torch.long)
+    assert torch.equal(masking.transfer_pixels(img, p1, p2).cpu(), T(g["transfer"]))
+    assert torch.equal(masking.transfer_pixels(img, p1, p2, rbound=torch.tensor([100, 400])).cpu(), T(g["transfer_rbound"]))
+
+
+def test_masking_reference_signature(native_lib, g, faces):
+    """masking(img, mask, extra_points, wr, rendered_mask, extra_noise, random_mask) (masking.py:71-102): deterministic
+    setting against the reference's own output; with the random draws on, structural checks."""
+    from oracle import masking_ref
+    from smirk_b200 import masking
+    npoints, rbound = T(g["npoints"], torch.long), T(g["rbound"])
+    img = synth_inputs.images(npoints.shape[0], int(g["seeds"][2]))
+    hull = T(g["hull"], torch.float32)
+    extra = img * masking_ref.point_mask_ref(npoints, rbound, 224)
+    out = masking.masking(img.to(DEV), hull, extra, 10, rendered_mask=None, extra_noise=False, random_mask=0, flame_faces=faces).cpu()
+    assert torch.equal(out[:, :, ::2, 1::2], T(g["masked_plain_sub"]))
+    torch.manual_seed(3)
+    rmask = T(g["rendered_img_nonzero"], torch.float32)
+    noisy = masking.masking(img.to(DEV), hull, extra, 10, rendered_mask=rmask, flame_faces=faces).cpu()
+    base = masking_ref.masking_ref(img, hull, extra, 10, rendered_mask=rmask)
+    sel = extra > 0
+    assert torch.equal(noisy[~sel], base[~sel])                         # only retained points see the draws
+    kept = noisy[sel] > 0
+    assert 0.5 < float(kept.float().mean()) <= 1.0                      # ~1 % centres x 11x11 patches knock some points out
+    ratio = (noisy[sel][kept] / extra[sel][kept])
+    assert abs(float(ratio.mean()) - 1) < 0.01 and abs(float(ratio.std()) - 0.05) < 0.01
