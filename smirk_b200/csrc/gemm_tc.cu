@@ -290,6 +290,13 @@ gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcArgs a) {
                 if (nc < a.N) {
                     const float4 sc = __ldg(reinterpret_cast<const float4*>(g_scale + nc));
                     const float4 bi = __ldg(reinterpret_cast<const float4*>(g_bias + nc));
+                    float hw[4][4];                            // store 3: this lane's 4 x head_c slice of the 1x1 head, loaded once per tile
+                    if (a.store == 3) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+#pragma unroll
+                            for (int co = 0; co < 4; ++co) hw[q][co] = co < a.head_c ? __ldg(a.head_w + (size_t)(nc + q) * a.head_c + co) : 0.f;
+                    }
                     int col = nc, pix_off = 0;
                     if (a.store == 1) {                        // ConvTranspose2d k2 s2: n = (dy*2+dx)*Cout + co
                         const int cout = a.N >> 2, q = nc / cout;
@@ -317,7 +324,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcArgs a) {
                             for (int q = 0; q < 4; ++q)
 #pragma unroll
                                 for (int co = 0; co < 4; ++co)
-                                    if (co < a.head_c) acc[co] = fmaf(xs[q], __ldg(a.head_w + (size_t)(nc + q) * a.head_c + co), acc[co]);
+                                    acc[co] = fmaf(xs[q], hw[q][co], acc[co]);
 #pragma unroll
                             for (int co = 0; co < 4; ++co) {
                                 acc[co] += __shfl_xor_sync(__activemask(), acc[co], 1);
@@ -511,7 +518,8 @@ int tc_conv(const TcConv& p, cudaStream_t st, const TcConv* p2) {
     if (groups == 1) { mp.a[1] = mp.a[0]; mp.b[1] = mp.b[0]; mp.blo[1] = mp.blo[0]; a.scale[1] = a.scale[0]; a.bias[1] = a.bias[0]; a.res[1] = a.res[0]; a.out[1] = a.out[0]; }
     {
         const double cin_eff = p.mode == 0 ? p.K : p.Cin;
-        const char* tag = p.mode == 0 ? (p.store == 1 ? "upconv_gemm_tc" : (p.wt_lo ? "pw_gemm_tc3x" : "pw_gemm_tc")) : "conv3x3_gemm_tc";
+        const char* tag = p.mode == 0 ? (p.store == 1 ? "upconv_gemm_tc" : (p.wt_lo ? "pw_gemm_tc3x" : "pw_gemm_tc"))
+                                      : (p.store == 3 ? "conv3x3_head_gemm_tc" : "conv3x3_gemm_tc");
         if (g_prof_detail) tag = prof_shape_tag(tag, (long)groups * M, p.K, p.N);
         SMK_TAG(tag,
                 groups * 4.0 * ((double)M * cin_eff + (double)p.K * p.N + (double)M * p.N * (p.res ? 2 : 1) + 2.0 * p.N),
@@ -520,6 +528,14 @@ int tc_conv(const TcConv& p, cudaStream_t st, const TcConv* p2) {
     if (p.wt_lo) {                                      // 3xTF32: fp32-equivalent arithmetic (encoder precision 3)
         // tails of the activations in tensor memory (default) or in shared memory (SMK_X3_TMEM=0: the first, larger-footprint cut)
         static const int x3_tmem = []() { const char* e = getenv("SMK_X3_TMEM"); return e ? atoi(e) : 1; }();
+        // deep-K layers (the 14x14 / 7x7 projections, K = 480..960): per k-block the chain TMA -> split -> MMA -> free is
+        // ~1.5 us with a 2-stage ring (measured: 47 us for K = 960); a 4-stage ring keeps three loads in flight
+        static const int x3_deep = []() { const char* e = getenv("SMK_X3_DEEP"); return e ? atoi(e) : 1; }();
+        if (x3_tmem && x3_deep && a.nkb >= 8) {
+            if (BN == 32) return launch<32, 4, 2, false, 2>(mp, a, st, groups);
+            if (BN == 64) return launch<64, 4, 1, false, 2>(mp, a, st, groups);
+            return launch<128, 4, 1, false, 2>(mp, a, st, groups);
+        }
         if (x3_tmem) {
             if (BN == 32) return launch<32, 2, 4, false, 2>(mp, a, st, groups);
             if (BN == 64) return launch<64, 2, 3, false, 2>(mp, a, st, groups);

@@ -219,6 +219,9 @@ mask_sample_kernel(const float* __restrict__ w, int F, int N, float ratio_mul, c
             int a = 0, c = F - 1;                       // first index with cdf > x
             while (a < c) { const int m = (a + c) >> 1; if (cdf[m] > x) c = m; else a = m + 1; }
             f = a;
+            // the segmented float scan may be non-monotone by an ulp at a segment seam: never hand out a zero-weight face
+            while (f < F - 1 && !(wb[f] > 0.f)) ++f;
+            while (f > 0 && !(wb[f] > 0.f)) --f;
         }
         float u = u01(r.y), v = u01(r.z);
         if (u + v > 1.f) { u = 1.f - u; v = 1.f - v; }  // masking.py:61-66: reflect into the triangle

@@ -199,14 +199,16 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
                     const int s = it % STAGES;
                     mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
                     if (X3 == 2) {
-                        // thread = window row t of each half (its TMEM lane): heads rewritten in place, tails -> tensor memory
+                        // thread = window row r of each half = its TMEM lane (a warp may only touch lane quarter warp % 4):
+                        // heads rewritten in place, tails -> tensor memory
+                        const int r = (warp & 3) * 32 + lane;
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
-                            uint8_t* row = smem + s * STAGE_BYTES + half * HALF_BYTES + t * 128;
+                            uint8_t* row = smem + s * STAGE_BYTES + half * HALF_BYTES + r * 128;
                             float lo[32];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                float4* p = reinterpret_cast<float4*>(row + ((j ^ (t & 7)) << 4));
+                                float4* p = reinterpret_cast<float4*>(row + ((j ^ (r & 7)) << 4));
                                 const float4 v = *p;
                                 float4 hi;
                                 hi.x = round_tf32(v.x); hi.y = round_tf32(v.y); hi.z = round_tf32(v.z); hi.w = round_tf32(v.w);
