@@ -183,6 +183,11 @@ conv3_win_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
                             for (int co = 0; co < 4; ++co) hw[q][co] = co < a.head_c ? __ldg(a.head_w + (size_t)(nc + q) * a.head_c + co) : 0.f;
                     }
+                    float hb[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (a.store == 3) {
+#pragma unroll
+                        for (int co = 0; co < 4; ++co) if (co < a.head_c) hb[co] = __ldg(a.head_b + co);
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int r = 4 * i + sub;
@@ -194,22 +199,25 @@ conv3_win_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                             // fused 1x1 head + sigmoid (smirk_generator.py:77-78,86): N <= 32, so the 8 lanes of a row hold all of
                             // its activations; partial dot products, butterfly over the 8 lanes, lane 0 of the row stores NCHW.
                             // Every lane takes part in the shuffles (rows outside the image simply do not store).
-                            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
                             const float xs[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)
+                            for (int q = 0; q < 4; ++q) {
+                                a0 = fmaf(xs[q], hw[q][0], a0); a1 = fmaf(xs[q], hw[q][1], a1);
+                                a2 = fmaf(xs[q], hw[q][2], a2); a3 = fmaf(xs[q], hw[q][3], a3);
+                            }
 #pragma unroll
-                                for (int co = 0; co < 4; ++co) acc[co] = fmaf(xs[q], hw[q][co], acc[co]);
-#pragma unroll
-                            for (int co = 0; co < 4; ++co) {
-                                acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 1);
-                                acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 2);
-                                acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 4);
+                            for (int sft = 1; sft <= 4; sft <<= 1) {
+                                a0 += __shfl_xor_sync(0xffffffffu, a0, sft); a1 += __shfl_xor_sync(0xffffffffu, a1, sft);
+                                a2 += __shfl_xor_sync(0xffffffffu, a2, sft); a3 += __shfl_xor_sync(0xffffffffu, a3, sft);
                             }
                             if (jj == 0 && opix[i] >= 0) {
                                 const int hw_px = a.H * a.W, b = opix[i] / hw_px, rem = opix[i] - b * hw_px;
-                                for (int co = 0; co < a.head_c; ++co)
-                                    a.out[((size_t)b * a.head_c + co) * hw_px + rem] = 1.f / (1.f + __expf(-(acc[co] + __ldg(a.head_b + co))));
+                                float* dst = a.out + (size_t)b * a.head_c * hw_px + rem;
+                                dst[0] = 1.f / (1.f + __expf(-(a0 + hb[0])));
+                                if (a.head_c > 1) dst[hw_px] = 1.f / (1.f + __expf(-(a1 + hb[1])));
+                                if (a.head_c > 2) dst[2 * (size_t)hw_px] = 1.f / (1.f + __expf(-(a2 + hb[2])));
+                                if (a.head_c > 3) dst[3 * (size_t)hw_px] = 1.f / (1.f + __expf(-(a3 + hb[3])));
                             }
                             continue;
                         }

@@ -297,6 +297,11 @@ gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcArgs a) {
 #pragma unroll
                             for (int co = 0; co < 4; ++co) hw[q][co] = co < a.head_c ? __ldg(a.head_w + (size_t)(nc + q) * a.head_c + co) : 0.f;
                     }
+                    float hb[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (a.store == 3) {
+#pragma unroll
+                        for (int co = 0; co < 4; ++co) if (co < a.head_c) hb[co] = __ldg(a.head_b + co);
+                    }
                     int col = nc, pix_off = 0;
                     if (a.store == 1) {                        // ConvTranspose2d k2 s2: n = (dy*2+dx)*Cout + co
                         const int cout = a.N >> 2, q = nc / cout;
@@ -304,37 +309,40 @@ gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcArgs a) {
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        if (opix[i] < 0) continue;
+                        if (a.store != 3 && opix[i] < 0) continue;      // (store 3: every lane stays for the shuffles below)
                         const int r = 4 * i + sub;
                         const float4 x = *reinterpret_cast<const float4*>(slab + r * 128 + ((jj ^ (r & 7)) << 4));
                         float4 o;
                         o.x = fmaf(x.x, sc.x, bi.x); o.y = fmaf(x.y, sc.y, bi.y); o.z = fmaf(x.z, sc.z, bi.z); o.w = fmaf(x.w, sc.w, bi.w);
-                        if (g_res) {
+                        if (g_res && opix[i] >= 0) {
                             const float4 r4 = __ldg(reinterpret_cast<const float4*>(g_res + (size_t)rpix[i] * a.ld_res + nc));
                             o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
                         }
                         if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                         if (a.store == 3) {
-                            // fused 1x1 head + sigmoid (smirk_generator.py:77-78 -> :86): the 8 lanes of a row hold its N <= 32
-                            // activations, 4 each; partial dot products, butterfly over the 8 lanes, lane 0 of the row stores
-                            // NCHW.  The activation tensor itself is never written.
-                            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                            // fused 1x1 head + sigmoid (smirk_generator.py:77-78 -> :86), N == 32: the 8 lanes of a row hold its 32
+                            // activations, 4 each; partial dot products, butterfly over the 8 lanes (FULL-mask shuffles: the warp
+                            // is convergent here — a computed mask costs a warp-sync subroutine call per shuffle, measured 3.2x
+                            // on the whole layer), lane 0 of the row stores NCHW.  The activation tensor itself is never written.
+                            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
                             const float xs[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                                for (int co = 0; co < 4; ++co)
-                                    acc[co] = fmaf(xs[q], hw[q][co], acc[co]);
-#pragma unroll
-                            for (int co = 0; co < 4; ++co) {
-                                acc[co] += __shfl_xor_sync(__activemask(), acc[co], 1);
-                                acc[co] += __shfl_xor_sync(__activemask(), acc[co], 2);
-                                acc[co] += __shfl_xor_sync(__activemask(), acc[co], 4);
+                            for (int q = 0; q < 4; ++q) {
+                                a0 = fmaf(xs[q], hw[q][0], a0); a1 = fmaf(xs[q], hw[q][1], a1);
+                                a2 = fmaf(xs[q], hw[q][2], a2); a3 = fmaf(xs[q], hw[q][3], a3);
                             }
-                            if (jj == 0) {
-                                const int hw = a.H * a.W, b = opix[i] / hw, rem = opix[i] - b * hw;
-                                for (int co = 0; co < a.head_c; ++co)
-                                    g_out[((size_t)b * a.head_c + co) * hw + rem] = 1.f / (1.f + __expf(-(acc[co] + __ldg(a.head_b + co))));
+#pragma unroll
+                            for (int sft = 1; sft <= 4; sft <<= 1) {
+                                a0 += __shfl_xor_sync(0xffffffffu, a0, sft); a1 += __shfl_xor_sync(0xffffffffu, a1, sft);
+                                a2 += __shfl_xor_sync(0xffffffffu, a2, sft); a3 += __shfl_xor_sync(0xffffffffu, a3, sft);
+                            }
+                            if (jj == 0 && opix[i] >= 0) {
+                                const int hw_px = a.H * a.W, b = opix[i] / hw_px, rem = opix[i] - b * hw_px;
+                                float* dst = g_out + (size_t)b * a.head_c * hw_px + rem;
+                                dst[0] = 1.f / (1.f + __expf(-(a0 + hb[0])));
+                                if (a.head_c > 1) dst[hw_px] = 1.f / (1.f + __expf(-(a1 + hb[1])));
+                                if (a.head_c > 2) dst[2 * (size_t)hw_px] = 1.f / (1.f + __expf(-(a2 + hb[2])));
+                                if (a.head_c > 3) dst[3 * (size_t)hw_px] = 1.f / (1.f + __expf(-(a3 + hb[3])));
                             }
                             continue;
                         }
@@ -499,8 +507,8 @@ int tc_conv(const TcConv& p, cudaStream_t st, const TcConv* p2) {
     a.ld_res = p.ld_res; a.res_pad = p.res_pad; a.relu = p.relu;
     a.ld_out = p.ld_out; a.store = p.store; a.round_out = p.round_out;
     a.head_w = p.head_w; a.head_b = p.head_b; a.head_c = p.head_c;
-    SMK_REQUIRE(p.store != 3 || (p.N <= 32 && p.head_w && p.head_b && p.head_c >= 1 && p.head_c <= 4 && !p.res),
-                "tc_conv: the fused 1x1 head needs N <= 32 (one column tile) and 1..4 head channels");
+    SMK_REQUIRE(p.store != 3 || (p.N == 32 && p.head_w && p.head_b && p.head_c >= 1 && p.head_c <= 4 && !p.res),
+                "tc_conv: the fused 1x1 head needs N == 32 (one full column tile) and 1..4 head channels");
     SMK_REQUIRE(!p.wt_lo || (p.mode == 0 && p.store == 0), "tc_conv: the 3xTF32 path covers plain 1x1 convolutions / GEMMs");
     for (int g = 0; g < groups; ++g) {
         const TcConv& q = g ? *p2 : p;
@@ -530,8 +538,9 @@ int tc_conv(const TcConv& p, cudaStream_t st, const TcConv* p2) {
         // tails of the activations in tensor memory (default) or in shared memory (SMK_X3_TMEM=0: the first, larger-footprint cut)
         static const int x3_tmem = []() { const char* e = getenv("SMK_X3_TMEM"); return e ? atoi(e) : 1; }();
         // deep-K layers (the 14x14 / 7x7 projections, K = 480..960): per k-block the chain TMA -> split -> MMA -> free is
-        // ~1.5 us with a 2-stage ring (measured: 47 us for K = 960); a 4-stage ring keeps three loads in flight
-        static const int x3_deep = []() { const char* e = getenv("SMK_X3_DEEP"); return e ? atoi(e) : 1; }();
+        // ~1.5 us with a 2-stage ring (measured: 47 us for K = 960); a 4-stage ring keeps three loads in flight and is
+        // faster alone, but its footprint costs the concurrent pipeline 3 % (29.8k vs 30.6k faces/s): opt-in, SMK_X3_DEEP=1
+        static const int x3_deep = []() { const char* e = getenv("SMK_X3_DEEP"); return e ? atoi(e) : 0; }();
         if (x3_tmem && x3_deep && a.nkb >= 8) {
             if (BN == 32) return launch<32, 4, 2, false, 2>(mp, a, st, groups);
             if (BN == 64) return launch<64, 4, 1, false, 2>(mp, a, st, groups);

@@ -169,7 +169,7 @@ def test_masking_reference_signature(native_lib, g, faces):
     base = masking_ref.masking_ref(img, hull, extra, 10, rendered_mask=rmask)
     sel = extra > 0
     assert torch.equal(noisy[~sel], base[~sel])                         # only retained points see the draws
-    kept = noisy[sel] > 0
-    assert 0.5 < float(kept.float().mean()) <= 1.0                      # ~1 % centres x 11x11 patches knock some points out
-    ratio = (noisy[sel][kept] / extra[sel][kept])
+    knocked = noisy[sel] == base[sel]                                   # a knocked-out point falls back to img * mask
+    assert 0.3 < float(knocked.float().mean()) < 0.95                   # 1 % centres x 11x11 patches cover ~70 % of the image
+    ratio = noisy[sel][~knocked] / extra[sel][~knocked]
     assert abs(float(ratio.mean()) - 1) < 0.01 and abs(float(ratio.std()) - 0.05) < 0.01
