@@ -58,6 +58,8 @@ struct TcArgs {
     int store;                     // 0 plain, 1 pixel-shuffle (N = 4*Cout), 2 interior of a (H+2)x(W+2) padded buffer,
                                    // 3 fused head: out[b, co, h, w] = sigmoid(head_b[co] + sum_n act[m, n] * head_w[n][co]) (NCHW, N <= 32)
     int round_out;                 // 1: round the stored activations to TF32 (round-to-nearest) for the next tensor-core layer
+    int x3_trunc;                  // 3xTF32, tails in TMEM: 1 = rely on the tensor core TRUNCATING fp32 words to TF32 (head = a & ~0x1fff is
+                                   // implicit, nothing is written back to shared memory); 0 = rewrite the heads (round-to-nearest) in place
     const float* head_w; const float* head_b; int head_c;      // store 3: 1x1 head weights [N][head_c], bias [head_c], head_c <= 4
 };
 
@@ -205,17 +207,26 @@ gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcArgs a) {
                 mbar_wait(&full[s], (uint32_t)(kb / STAGES) & 1u);
                 uint8_t* row = smem + s * STAGE_BYTES + r * 128;
                 float lo[32];
+                if (a.x3_trunc) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4* p = reinterpret_cast<float4*>(row + ((j ^ (r & 7)) << 4));       // 16-byte chunk j of the row (SWIZZLE_128B)
-                    const float4 v = *p;
-                    float4 hi;
-                    hi.x = smk::round_tf32(v.x); hi.y = smk::round_tf32(v.y); hi.z = smk::round_tf32(v.z); hi.w = smk::round_tf32(v.w);
-                    lo[4 * j] = v.x - hi.x; lo[4 * j + 1] = v.y - hi.y; lo[4 * j + 2] = v.z - hi.z; lo[4 * j + 3] = v.w - hi.w;
-                    *p = hi;
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 v = *reinterpret_cast<const float4*>(row + ((j ^ (r & 7)) << 4));
+                        lo[4 * j] = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo[4 * j + 1] = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                        lo[4 * j + 2] = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo[4 * j + 3] = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4* p = reinterpret_cast<float4*>(row + ((j ^ (r & 7)) << 4));       // 16-byte chunk j of the row (SWIZZLE_128B)
+                        const float4 v = *p;
+                        float4 hi;
+                        hi.x = smk::round_tf32(v.x); hi.y = smk::round_tf32(v.y); hi.z = smk::round_tf32(v.z); hi.w = smk::round_tf32(v.w);
+                        lo[4 * j] = v.x - hi.x; lo[4 * j + 1] = v.y - hi.y; lo[4 * j + 2] = v.z - hi.z; lo[4 * j + 3] = v.w - hi.w;
+                        *p = hi;
+                    }
                 }
                 tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ALO_COL + (uint32_t)(s * 32), lo);   // warp-collective, waits for completion
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (!a.x3_trunc) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&split[s]);
@@ -507,6 +518,10 @@ int tc_conv(const TcConv& p, cudaStream_t st, const TcConv* p2) {
     a.ld_res = p.ld_res; a.res_pad = p.res_pad; a.relu = p.relu;
     a.ld_out = p.ld_out; a.store = p.store; a.round_out = p.round_out;
     a.head_w = p.head_w; a.head_b = p.head_b; a.head_c = p.head_c;
+    {
+        static const int x3_trunc = []() { const char* e = getenv("SMK_X3_TRUNC"); return e ? atoi(e) : 0; }();
+        a.x3_trunc = x3_trunc;
+    }
     SMK_REQUIRE(p.store != 3 || (p.N == 32 && p.head_w && p.head_b && p.head_c >= 1 && p.head_c <= 4 && !p.res),
                 "tc_conv: the fused 1x1 head needs N == 32 (one full column tile) and 1..4 head channels");
     SMK_REQUIRE(!p.wt_lo || (p.mode == 0 && p.store == 0), "tc_conv: the 3xTF32 path covers plain 1x1 convolutions / GEMMs");

@@ -65,6 +65,7 @@ struct XdwArgs {
     const float* scale2[2]; const float* bias2[2];  // folded BN of the depthwise conv   [mid]
     float* out[2];                                  // d: [B, Ho, Wo, mid]
     int round_out;
+    int x3_trunc;                  // see gemm_tc.cu: 1 = the tensor core's own truncation of fp32 words is the head
 };
 
 // X3 = true: error-compensated 3xTF32 expand GEMM (fp32-equivalent e): x = x_hi + x_lo split in shared memory by four
@@ -74,7 +75,7 @@ struct XdwArgs {
 // are multiplied with the A-from-TMEM form of tcgen05.mma — shared memory stays at the plain kernel's 113 KB + the weight
 // tails, so the SM keeps room for the other kernels of the concurrent pipeline.
 template <int STRIDE, int X3>
-__global__ void __launch_bounds__(NUM_THREADS + (X3 ? NUM_SPLITTERS : 0), X3 ? 1 : 2)
+__global__ void __launch_bounds__(NUM_THREADS + (X3 ? NUM_SPLITTERS : 0), X3 ? 1 : 2) __maxnreg__(X3 ? 96 : 102)
 xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
     constexpr int TO = STRIDE == 1 ? 14 : 7;                    // output tile edge
     constexpr int STAGE_BYTES = X3 == 1 ? 2 * smk::STAGE_BYTES : (X3 == 2 ? smk::STAGE_BYTES + B_BYTES : smk::STAGE_BYTES);
@@ -206,18 +207,27 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
                         for (int half = 0; half < 2; ++half) {
                             uint8_t* row = smem + s * STAGE_BYTES + half * HALF_BYTES + r * 128;
                             float lo[32];
+                            if (a.x3_trunc) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float4* p = reinterpret_cast<float4*>(row + ((j ^ (r & 7)) << 4));
-                                const float4 v = *p;
-                                float4 hi;
-                                hi.x = round_tf32(v.x); hi.y = round_tf32(v.y); hi.z = round_tf32(v.z); hi.w = round_tf32(v.w);
-                                lo[4 * j] = v.x - hi.x; lo[4 * j + 1] = v.y - hi.y; lo[4 * j + 2] = v.z - hi.z; lo[4 * j + 3] = v.w - hi.w;
-                                *p = hi;
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 v = *reinterpret_cast<const float4*>(row + ((j ^ (r & 7)) << 4));
+                                    lo[4 * j] = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo[4 * j + 1] = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                                    lo[4 * j + 2] = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo[4 * j + 3] = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    float4* p = reinterpret_cast<float4*>(row + ((j ^ (r & 7)) << 4));
+                                    const float4 v = *p;
+                                    float4 hi;
+                                    hi.x = round_tf32(v.x); hi.y = round_tf32(v.y); hi.z = round_tf32(v.z); hi.w = round_tf32(v.w);
+                                    lo[4 * j] = v.x - hi.x; lo[4 * j + 1] = v.y - hi.y; lo[4 * j + 2] = v.z - hi.z; lo[4 * j + 3] = v.w - hi.w;
+                                    *p = hi;
+                                }
                             }
                             tmem_st32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + XLO_COL + (uint32_t)((s * 2 + half) * 32), lo);
                         }
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        if (!a.x3_trunc) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         tcgen05_fence_before();
                     } else {
                         float4* X = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
@@ -464,6 +474,10 @@ int xdw_conv(const XdwConv& p, cudaStream_t st, const XdwConv* p2) {
     a.pad = p.stride == 1 ? 1 : 0;
     a.tiles_x = cdiv(Wo, TO); a.tiles_y = cdiv(Ho, TO);
     a.round_out = p.round_out;
+    {
+        static const int x3_trunc = []() { const char* e = getenv("SMK_X3_TRUNC"); return e ? atoi(e) : 0; }();
+        a.x3_trunc = x3_trunc;
+    }
     constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + E_BYTES + PAR_BYTES + 1024 + 256;
     constexpr size_t smem3 = (size_t)STAGES * 2 * STAGE_BYTES + E_BYTES + PAR_BYTES + 1024 + 256;          // tails in shared memory
     constexpr size_t smem3t = (size_t)STAGES * (STAGE_BYTES + B_BYTES) + E_BYTES + PAR_BYTES + 1024 + 256;  // tails in tensor memory
