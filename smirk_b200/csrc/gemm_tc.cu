@@ -255,6 +255,14 @@ gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcArgs a) {
         }
         uint8_t* slab = slabs + quarter * 4096;
         const int sub = lane >> 3, jj = lane & 7;              // phase-2 role: row-in-group, 16-byte chunk
+        if (a.store == 3) {                                    // head constants of channel `lane` -> this warp's slab (PERSIST layout: slabs are private)
+            float* par = reinterpret_cast<float*>(slab);
+            par[lane * 8 + 0] = __ldg(a.scale[0] + lane); par[lane * 8 + 1] = __ldg(a.bias[0] + lane);
+#pragma unroll
+            for (int co = 0; co < 4; ++co) par[lane * 8 + 2 + co] = co < a.head_c ? __ldg(a.head_w + (size_t)lane * a.head_c + co) : 0.f;
+            if (lane < 4) par[256 + lane] = lane < a.head_c ? __ldg(a.head_b + lane) : 0.f;
+            __syncwarp();
+        }
         int tc = 0;
         for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++tc) {
             const int g = t >= a.n_tiles_g ? 1 : 0, tt = t - g * a.n_tiles_g;
@@ -293,6 +301,32 @@ gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcArgs a) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
+                if (a.store == 3) {
+                    // Fused 1x1 head + sigmoid (smirk_generator.py:77-78 -> :86), N == BN == 32: right after tcgen05.ld every lane holds
+                    // ALL 32 accumulators of its own pixel, so BN + ReLU + the 32 -> head_c dot products need no exchange between
+                    // lanes; per-channel constants come from this warp's slab (filled once, broadcast LDS), consecutive lanes are
+                    // consecutive pixels -> coalesced NCHW stores.  The activation tensor itself is never written.
+                    const float* par = reinterpret_cast<const float*>(slab);       // [32][8]: scale, bias, w0..w3, pad
+                    float a0 = par[256], a1 = par[257], a2 = par[258], a3 = par[259];       // head bias
+#pragma unroll
+                    for (int nn = 0; nn < 32; ++nn) {
+                        const float4 p0 = *reinterpret_cast<const float4*>(par + nn * 8);
+                        const float2 p1 = *reinterpret_cast<const float2*>(par + nn * 8 + 4);
+                        float x = fmaf(v[nn], p0.x, p0.y);
+                        if (a.relu) x = fmaxf(x, 0.f);
+                        a0 = fmaf(x, p0.z, a0); a1 = fmaf(x, p0.w, a1); a2 = fmaf(x, p1.x, a2); a3 = fmaf(x, p1.y, a3);
+                    }
+                    const int m = m0 + quarter * 32 + lane;
+                    if (m < a.M) {
+                        const int hw_px = a.H * a.W, b = m / hw_px, rem = m - b * hw_px;
+                        float* dst = g_out + (size_t)b * a.head_c * hw_px + rem;
+                        dst[0] = 1.f / (1.f + __expf(-a0));
+                        if (a.head_c > 1) dst[hw_px] = 1.f / (1.f + __expf(-a1));
+                        if (a.head_c > 2) dst[2 * (size_t)hw_px] = 1.f / (1.f + __expf(-a2));
+                        if (a.head_c > 3) dst[3 * (size_t)hw_px] = 1.f / (1.f + __expf(-a3));
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<float4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -301,18 +335,6 @@ gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcArgs a) {
                 if (nc < a.N) {
                     const float4 sc = __ldg(reinterpret_cast<const float4*>(g_scale + nc));
                     const float4 bi = __ldg(reinterpret_cast<const float4*>(g_bias + nc));
-                    float hw[4][4];                            // store 3: this lane's 4 x head_c slice of the 1x1 head, loaded once per tile
-                    if (a.store == 3) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-#pragma unroll
-                            for (int co = 0; co < 4; ++co) hw[q][co] = co < a.head_c ? __ldg(a.head_w + (size_t)(nc + q) * a.head_c + co) : 0.f;
-                    }
-                    float hb[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (a.store == 3) {
-#pragma unroll
-                        for (int co = 0; co < 4; ++co) if (co < a.head_c) hb[co] = __ldg(a.head_b + co);
-                    }
                     int col = nc, pix_off = 0;
                     if (a.store == 1) {                        // ConvTranspose2d k2 s2: n = (dy*2+dx)*Cout + co
                         const int cout = a.N >> 2, q = nc / cout;
@@ -320,43 +342,16 @@ gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcArgs a) {
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        if (a.store != 3 && opix[i] < 0) continue;      // (store 3: every lane stays for the shuffles below)
+                        if (opix[i] < 0) continue;
                         const int r = 4 * i + sub;
                         const float4 x = *reinterpret_cast<const float4*>(slab + r * 128 + ((jj ^ (r & 7)) << 4));
                         float4 o;
                         o.x = fmaf(x.x, sc.x, bi.x); o.y = fmaf(x.y, sc.y, bi.y); o.z = fmaf(x.z, sc.z, bi.z); o.w = fmaf(x.w, sc.w, bi.w);
-                        if (g_res && opix[i] >= 0) {
+                        if (g_res) {
                             const float4 r4 = __ldg(reinterpret_cast<const float4*>(g_res + (size_t)rpix[i] * a.ld_res + nc));
                             o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
                         }
                         if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        if (a.store == 3) {
-                            // fused 1x1 head + sigmoid (smirk_generator.py:77-78 -> :86), N == 32: the 8 lanes of a row hold its 32
-                            // activations, 4 each; partial dot products, butterfly over the 8 lanes (FULL-mask shuffles: the warp
-                            // is convergent here — a computed mask costs a warp-sync subroutine call per shuffle, measured 3.2x
-                            // on the whole layer), lane 0 of the row stores NCHW.  The activation tensor itself is never written.
-                            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                            const float xs[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                a0 = fmaf(xs[q], hw[q][0], a0); a1 = fmaf(xs[q], hw[q][1], a1);
-                                a2 = fmaf(xs[q], hw[q][2], a2); a3 = fmaf(xs[q], hw[q][3], a3);
-                            }
-#pragma unroll
-                            for (int sft = 1; sft <= 4; sft <<= 1) {
-                                a0 += __shfl_xor_sync(0xffffffffu, a0, sft); a1 += __shfl_xor_sync(0xffffffffu, a1, sft);
-                                a2 += __shfl_xor_sync(0xffffffffu, a2, sft); a3 += __shfl_xor_sync(0xffffffffu, a3, sft);
-                            }
-                            if (jj == 0 && opix[i] >= 0) {
-                                const int hw_px = a.H * a.W, b = opix[i] / hw_px, rem = opix[i] - b * hw_px;
-                                float* dst = g_out + (size_t)b * a.head_c * hw_px + rem;
-                                dst[0] = 1.f / (1.f + __expf(-(a0 + hb[0])));
-                                if (a.head_c > 1) dst[hw_px] = 1.f / (1.f + __expf(-(a1 + hb[1])));
-                                if (a.head_c > 2) dst[2 * (size_t)hw_px] = 1.f / (1.f + __expf(-(a2 + hb[2])));
-                                if (a.head_c > 3) dst[3 * (size_t)hw_px] = 1.f / (1.f + __expf(-(a3 + hb[3])));
-                            }
-                            continue;
-                        }
                         if (a.round_out) { o.x = smk::round_tf32(o.x); o.y = smk::round_tf32(o.y); o.z = smk::round_tf32(o.z); o.w = smk::round_tf32(o.w); }
                         *reinterpret_cast<float4*>(g_out + (size_t)(opix[i] + pix_off) * a.ld_out + col) = o;
                     }
@@ -478,7 +473,6 @@ int tc_init() { return load_driver_fns(); }
 
 int tc_conv(const TcConv& p, cudaStream_t st, const TcConv* p2) {
     if (int rc = load_driver_fns()) return rc;
-    if (!p2 && conv3_win_supported(p)) return conv3_win(p, st);       // 224^2 / 112^2, Cout 32 / 64: one patch load per chunk, resident weights
     const int M = p.B * p.H * p.W;
     const int groups = p2 ? 2 : 1;
     SMK_REQUIRE(p.N % 4 == 0 && p.K % 4 == 0 && p.ld_in % 4 == 0 && p.ld_out % 4 == 0, "tc_conv: N, K, ld must be multiples of 4");
@@ -519,11 +513,11 @@ int tc_conv(const TcConv& p, cudaStream_t st, const TcConv* p2) {
     a.ld_out = p.ld_out; a.store = p.store; a.round_out = p.round_out;
     a.head_w = p.head_w; a.head_b = p.head_b; a.head_c = p.head_c;
     {
-        static const int x3_trunc = []() { const char* e = getenv("SMK_X3_TRUNC"); return e ? atoi(e) : 0; }();
+        static const int x3_trunc = []() { const char* e = getenv("SMK_X3_TRUNC"); return e ? atoi(e) : 1; }();
         a.x3_trunc = x3_trunc;
     }
-    SMK_REQUIRE(p.store != 3 || (p.N == 32 && p.head_w && p.head_b && p.head_c >= 1 && p.head_c <= 4 && !p.res),
-                "tc_conv: the fused 1x1 head needs N == 32 (one full column tile) and 1..4 head channels");
+    SMK_REQUIRE(p.store != 3 || (p.N == 32 && p.mode != 0 && p.head_w && p.head_b && p.head_c >= 1 && p.head_c <= 4 && !p.res && !p2),
+                "tc_conv: the fused 1x1 head needs a 3x3 conv with N == 32 (persistent kernel, one full column tile) and 1..4 head channels");
     SMK_REQUIRE(!p.wt_lo || (p.mode == 0 && p.store == 0), "tc_conv: the 3xTF32 path covers plain 1x1 convolutions / GEMMs");
     for (int g = 0; g < groups; ++g) {
         const TcConv& q = g ? *p2 : p;
@@ -576,7 +570,7 @@ int tc_conv(const TcConv& p, cudaStream_t st, const TcConv* p2) {
     const long n_tiles = (long)groups * cdiv(M, BM) * cdiv(p.N, BN);
     // 3x3 convolutions (deep K): persistent CTAs for the narrow-N layers and for the few-tile 14x14 layers;
     // the wide-N layers are bound by the shared-memory fill rate either way and keep two single-tile CTAs per SM.
-    const bool persist = persist_mode >= 0 ? persist_mode != 0 : (p.mode != 0 && (BN <= 64 || n_tiles <= 2 * 148));
+    const bool persist = p.store == 3 || (persist_mode >= 0 ? persist_mode != 0 : (p.mode != 0 && (BN <= 64 || n_tiles <= 2 * 148)));   // (the fused head lives in the persistent layout: private slabs)
     if (BN == 256) return launch<256, 4, 1, true>(mp, a, st, groups);
     if (persist) {
         if (BN == 32) return launch<32, 4, 2, true>(mp, a, st, groups);

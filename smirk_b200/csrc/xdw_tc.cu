@@ -475,7 +475,7 @@ int xdw_conv(const XdwConv& p, cudaStream_t st, const XdwConv* p2) {
     a.tiles_x = cdiv(Wo, TO); a.tiles_y = cdiv(Ho, TO);
     a.round_out = p.round_out;
     {
-        static const int x3_trunc = []() { const char* e = getenv("SMK_X3_TRUNC"); return e ? atoi(e) : 0; }();
+        static const int x3_trunc = []() { const char* e = getenv("SMK_X3_TRUNC"); return e ? atoi(e) : 1; }();
         a.x3_trunc = x3_trunc;
     }
     constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + E_BYTES + PAR_BYTES + 1024 + 256;
