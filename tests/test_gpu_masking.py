@@ -171,5 +171,7 @@ def test_masking_reference_signature(native_lib, g, faces):
     assert torch.equal(noisy[~sel], base[~sel])                         # only retained points see the draws
     knocked = noisy[sel] == base[sel]                                   # a knocked-out point falls back to img * mask
     assert 0.05 < float(knocked.float().mean()) < 0.95                  # 1 % centres x 11x11 patches cover ~70 % of the image; sampled points cluster
-    ratio = noisy[sel][~knocked] / extra[sel][~knocked]
+    kept = (noisy[sel] > 0) & ~knocked                                  # retained points that carry img * noise
+    assert float(kept.float().mean()) > 0.1
+    ratio = noisy[sel][kept] / extra[sel][kept]
     assert abs(float(ratio.mean()) - 1) < 0.01 and abs(float(ratio.std()) - 0.05) < 0.01
