@@ -15,3 +15,5 @@ for f in sorted(glob.glob('gpurun_out/r02_5_*.json')):
         d=json.loads(open(f).read().strip().splitlines()[-1]); print(f.split('r02_5_')[1], round(d['value']), round(d['e2e']['value']), d['config']['execution'][:34])
     except Exception as e: print(f,'ERR',e)
 PY
+for c in 1 2 3; do SMK_WIN_CTAS=$c timeout 300 python tools/bench_win.py 2>&1 | tail -3; done
+SMK_WIN_CTAS=2 timeout 300 python tools/bench_win.py --cin 64 2>&1 | tail -3
