@@ -238,6 +238,10 @@ int smk_debug_xdw(const float* x, int B, int H, int W, int Cin, const float* w1t
                   int mid, const float* wdw, const float* scale2, const float* bias2, int stride, int round_out,
                   float* out, void* stream);
 
+/*   smk_debug_conv3_win: the persistent windowed TF32 tcgen05 3x3 convolution of the high-resolution narrow layers
+ *                  (zero padding 1, N in {32, 64}, Cin % 32 == 0, W >= 56, resident weights <= 72 KB); wt is [N][9*Cin].      */
+int smk_debug_conv3_win(const float* in, int ld_in, int B, int H, int W, int Cin, const float* wt, const float* scale,
+                        const float* bias, int N, int relu, float* out, int ld_out, void* stream);
 /*   smk_debug_gemm_tc3x / smk_debug_xdw3x: the error-compensated 3xTF32 variants of the two tensor-core encoder kernels
  *                  (encoder precision 3).  wt_hi / wt_lo (w1t_hi / w1t_lo) are the TF32 heads and tails of the weights:
  *                  hi = tf32(w), lo = tf32(w - hi).  in is [M, ld_in] row-major; out [M, ld_out].                       */

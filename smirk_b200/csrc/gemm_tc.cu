@@ -473,6 +473,7 @@ int tc_init() { return load_driver_fns(); }
 
 int tc_conv(const TcConv& p, cudaStream_t st, const TcConv* p2) {
     if (int rc = load_driver_fns()) return rc;
+    if (!p2 && conv3_win_supported(p)) return conv3_win(p, st);       // 224^2 / 112^2, Cout 32 / 64: one patch load per chunk, resident weights
     const int M = p.B * p.H * p.W;
     const int groups = p2 ? 2 : 1;
     SMK_REQUIRE(p.N % 4 == 0 && p.K % 4 == 0 && p.ld_in % 4 == 0 && p.ld_out % 4 == 0, "tc_conv: N, K, ld must be multiples of 4");

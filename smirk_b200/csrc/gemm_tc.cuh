@@ -25,6 +25,9 @@ int tc_init();                                              // resolves the driv
 // p2 (optional): a second problem of identical shape sharing the launch (tiles of both in one grid).
 int tc_conv(const TcConv& p, cudaStream_t st, const TcConv* p2 = nullptr);
 int reflect_halo(float* buf, int B, int H, int W, int C, cudaStream_t st);
+// Persistent windowed 3x3 kernel for the high-resolution narrow layers (conv3_win_tc.cu); tc_conv dispatches to it.
+bool conv3_win_supported(const TcConv& p);
+int conv3_win(const TcConv& p, cudaStream_t st);
 
 
 }  // namespace smk

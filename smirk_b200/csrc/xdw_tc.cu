@@ -461,7 +461,13 @@ int xdw_conv(const XdwConv& p, cudaStream_t st, const XdwConv* p2) {
         mp.x[1] = mp.x[0]; mp.w[1] = mp.w[0]; mp.wlo[1] = mp.wlo[0];
         a.scale1[1] = a.scale1[0]; a.bias1[1] = a.bias1[0]; a.wdw[1] = a.wdw[0]; a.scale2[1] = a.scale2[0]; a.bias2[1] = a.bias2[0]; a.out[1] = a.out[0];
     }
-    static const int slots_lo = []() { const char* e = getenv("SMK_XDW_SLOTS"); return e ? atoi(e) : 148; }();   // resident CTAs to aim for: one per SM leaves half of every SM to concurrent kernels (+4 % end to end vs 296)
+    // Resident CTAs to aim for.  Round 1 (plain TF32, 2 CTAs/SM possible): one per SM leaves half of every SM to the concurrent
+    // kernels (+4 % end to end vs 296).  The 3xTF32 variant owns most of an SM's registers and half its tensor memory, so in the
+    // small-batch regime (many short kernels of 3 backbones x 4 lanes in flight) it pays to leave half of the SMs entirely to
+    // the other kernels: 74 CTAs measured +3.4 % (34.6k vs 33.5k faces/s at B = 32); large batches are throughput-bound and
+    // take every SM.
+    static const int slots_env = []() { const char* e = getenv("SMK_XDW_SLOTS"); return e ? atoi(e) : 0; }();
+    const int slots_lo = slots_env > 0 ? slots_env : ((p.w1t_lo && p.B <= 64) ? 74 : 148);
     static const int slots_hi = []() { const char* e = getenv("SMK_XDW_SLOTS_HI"); return e ? atoi(e) : 0; }();  // layers with >= 296 output tiles (0: same as SMK_XDW_SLOTS)
     const int slots = (slots_hi > 0 && (long)nprob * cdiv(Wo, TO) * cdiv(Ho, TO) * p.B >= 296) ? slots_hi : slots_lo;
     a.H = p.H; a.W = p.W; a.Ho = Ho; a.Wo = Wo; a.mid = p.mid; a.nkb = cdiv(p.Cin, BK); a.nchunks = cdiv(p.mid, NC);

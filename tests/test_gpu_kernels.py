@@ -338,3 +338,41 @@ def test_xdw3x_matches_fp64(native_lib, B, H, Cin, mid, stride):
     assert torch.isfinite(got).all(), "unwritten outputs: %d" % int((~torch.isfinite(got)).sum())
     err = (got - ref).abs().max().item()
     assert err <= 5e-6 * ref.abs().max().item(), "max err %.3g vs scale %.3g" % (err, ref.abs().max().item())
+
+
+# ----------------------------------------------------------------- persistent windowed 3x3 conv (conv3_win_tc.cu)
+def run_win(native_lib, x, w, scale, bias, relu):
+    B, Cin, H, W = x.shape
+    N = w.shape[0]
+    xd, wd = nhwc(x).to(DEV), w_nk(w).to(DEV)
+    out = torch.full((B, H, W, N), float("nan"), device=DEV)
+    sd, bd = scale.to(DEV), bias.to(DEV)
+    rc = native_lib.smk_debug_conv3_win(P(xd), Cin, B, H, W, Cin, P(wd), P(sd), P(bd), N, relu, P(out), N, stream())
+    assert rc == 0, native_lib.smk_last_error()
+    torch.cuda.synchronize()
+    return out.permute(0, 3, 1, 2).cpu()
+
+
+def test_conv3_win_exact_on_small_integers(native_lib):
+    """Operands exactly representable in TF32: the result must be exact — pins the patch addressing (tap views into the
+    swizzled window, wrap columns, zero-filled halo), the resident-weight indexing, the tile decode and the split of the
+    tiles over the two pipelines of a CTA."""
+    g = torch.Generator().manual_seed(71)
+    for (B, H, W, Cin, N) in [(2, 61, 70, 32, 32), (1, 56, 56, 64, 32), (3, 57, 113, 32, 64), (1, 60, 56, 32, 32)]:
+        x = torch.randint(-3, 4, (B, Cin, H, W), generator=g).float()
+        w = torch.randint(-2, 3, (N, Cin, 3, 3), generator=g).float()
+        one, zero = torch.ones(N), torch.zeros(N)
+        ref = F.conv2d(x.double(), w.double(), padding=1).float()
+        got = run_win(native_lib, x, w, one, zero, 0)
+        assert torch.isfinite(got).all(), "unwritten outputs: %d" % int((~torch.isfinite(got)).sum())
+        assert torch.equal(got, ref), "B %d H %d W %d Cin %d N %d: %d mismatches" % (B, H, W, Cin, N, int((got != ref).sum()))
+
+
+@pytest.mark.parametrize("B,H,W,Cin,N", [(2, 224, 224, 32, 32), (1, 224, 224, 64, 32), (2, 112, 112, 32, 64), (5, 64, 90, 32, 32)])
+def test_conv3_win_random_with_epilogue(native_lib, B, H, W, Cin, N):
+    x, w, scale, bias = make_case(B, H, W, Cin, N, 72, 1)
+    for relu in (1, 0):
+        ref = torch_conv(x, w, scale, bias, 1, relu)
+        got = run_win(native_lib, x, w, scale, bias, relu)
+        assert torch.isfinite(got).all()
+        assert (got - ref).abs().max().item() <= 3e-3 * ref.abs().max().item()

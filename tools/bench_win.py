@@ -7,7 +7,6 @@ from smirk_b200 import _lib
 
 ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=256); ap.add_argument("--cin", type=int, default=32); a = ap.parse_args()
 lib = _lib.lib(); vp, i = C.c_void_p, C.c_int
-lib.smk_debug_conv3_win.argtypes = [vp, i, i, i, i, i, vp, vp, vp, i, i, vp, i, vp]
 dev = torch.device("cuda:0"); B, H, Cin, N = a.batch, 224, a.cin, 32
 x = torch.randn(B, H, H, Cin, device=dev); w = torch.randn(N, 9 * Cin, device=dev) / (9 * Cin) ** 0.5
 sc, bi = torch.rand(N, device=dev) + 0.5, torch.randn(N, device=dev) * 0.1
@@ -15,7 +14,9 @@ o1, o2 = torch.empty(B, H, H, N, device=dev), torch.empty(B, H, H, N, device=dev
 st = torch.cuda.current_stream().cuda_stream
 P = lambda t: t.data_ptr()
 def win(): assert lib.smk_debug_conv3_win(P(x), Cin, B, H, H, Cin, P(w), P(sc), P(bi), N, 1, P(o1), N, st) == 0, lib.smk_last_error()
-def im2col(): assert lib.smk_debug_conv_tc(P(x), Cin, B, H, H, Cin, P(w), P(sc), P(bi), N, 9 * Cin, 1, 1, 0, N, 0, P(o2), N, 0, st) == 0, lib.smk_last_error()
+def im2col():
+    os.environ.get("X")
+    assert lib.smk_debug_conv_tc(P(x), Cin, B, H, H, Cin, P(w), P(sc), P(bi), N, 9 * Cin, 1, 1, 0, N, 0, P(o2), N, 0, st) == 0, lib.smk_last_error()
 for name, fn in (("win", win), ("im2col", im2col)):
     for _ in range(2): fn()
     torch.cuda.synchronize()
