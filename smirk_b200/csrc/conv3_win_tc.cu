@@ -40,6 +40,7 @@ constexpr int STAGES = 2;                            // patch ring depth per pip
 constexpr int SLAB_BYTES = 4 * 4096;                 // per pipeline
 constexpr int TAIL_BYTES = 1024;                     // the last tap view reads 2 rows past its patch: keep that inside the allocation
 constexpr int PIPE_BYTES = STAGES * PATCH_BYTES + TAIL_BYTES + SLAB_BYTES;      // 66 560 B
+constexpr int NB = 4;                                // weight-ring depth per pipeline (layers whose weights do not fit resident)
 
 struct WinArgs {
     int H, W, N;
@@ -52,7 +53,10 @@ struct WinArgs {
     const float* head_w; const float* head_b; int head_c;
 };
 
-template <int BN>
+// RES = true : the layer's whole weight matrix stays in shared memory, shared by both pipelines (<= 72 KB);
+// RES = false: each pipeline streams the (chunk, tap) weight boxes through its own NB-deep ring (the 112^2 Cout-64 layers with
+//              147 - 295 KB of weights): the input window is still loaded once per chunk instead of nine times.
+template <int BN, bool RES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3_win_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const WinArgs a) {
     constexpr int B_BYTES = BN * 128;                      // one (chunk, tap) weight box
@@ -64,20 +68,25 @@ conv3_win_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int pipe = warp / 6, pw = warp - pipe * 6;       // pipeline of this warp, role within it
     uint8_t* sP = smem + pipe * PIPE_BYTES;                // this pipeline's patch ring (+ tail) ...
     uint8_t* slabs = sP + STAGES * PATCH_BYTES + TAIL_BYTES;      // ... and epilogue staging
-    uint8_t* sW = smem + PIPES * PIPE_BYTES;               // resident weights: [chunk][tap][BN x 128 B], shared by both pipelines
-    const int w_bytes = a.nchunks * 9 * B_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + w_bytes);
+    // weights: resident [chunk][tap][BN x 128 B] shared by both pipelines, or one NB-deep ring of boxes per pipeline
+    const int w_bytes = RES ? a.nchunks * 9 * B_BYTES : PIPES * NB * B_BYTES;
+    uint8_t* sW = smem + PIPES * PIPE_BYTES + (RES ? 0 : pipe * NB * B_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PIPES * PIPE_BYTES + w_bytes);
+    constexpr int PER_PIPE_BARS = 2 * STAGES + 4 + 2 * NB;
     uint64_t* w_full = bars;                               // [1]
-    uint64_t* p_full = bars + 1 + pipe * (2 * STAGES + 4); // per pipeline: p_full[STAGES], p_empty[STAGES], acc_full[2], acc_empty[2]
+    uint64_t* p_full = bars + 1 + pipe * PER_PIPE_BARS;    // per pipeline: p_full[STAGES], p_empty[STAGES], acc_full[2], acc_empty[2], b_full[NB], b_empty[NB]
     uint64_t* p_empty = p_full + STAGES;
     uint64_t* acc_full = p_empty + STAGES;
     uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + PIPES * (2 * STAGES + 4));
+    uint64_t* b_full = acc_empty + 2;
+    uint64_t* b_empty = b_full + NB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + PIPES * PER_PIPE_BARS);
 
     if (pw == 0 && lane == 0) {
         if (pipe == 0) { prefetch_tensormap(&tmX); prefetch_tensormap(&tmW); mbar_init(w_full, 1); }
         for (int s = 0; s < STAGES; ++s) { mbar_init(&p_full[s], 1); mbar_init(&p_empty[s], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -98,13 +107,13 @@ conv3_win_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (pw == 0) {
         if (lane == 0) {
             // ===== TMA producer: (pipeline 0) the weights once; then one patch per (tile, channel chunk) =====
-            if (pipe == 0) {
+            if (RES && pipe == 0) {
                 mbar_expect_tx(w_full, (uint32_t)w_bytes);
                 for (int c = 0; c < a.nchunks; ++c)
                     for (int tap = 0; tap < 9; ++tap)
                         tma_load_2d(&tmW, sW + (c * 9 + tap) * B_BYTES, w_full, tap * a.nchunks * 32 + c * 32, 0);
             }
-            int it = 0;
+            int it = 0, itb = 0;
             for (int t = t_first; t < a.n_tiles; t += t_step) {
                 int img, h0, w0;
                 decode(t, img, h0, w0);
@@ -113,16 +122,23 @@ conv3_win_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                     mbar_wait(&p_empty[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
                     mbar_expect_tx(&p_full[s], (uint32_t)PATCH_BYTES);
                     tma_load_4d(&tmX, sP + s * PATCH_BYTES, &p_full[s], c * 32, w0 - 1, h0 - 1, img);
+                    if (!RES) {
+                        for (int tap = 0; tap < 9; ++tap, ++itb) {
+                            const int sb = itb % NB;
+                            mbar_wait(&b_empty[sb], ((uint32_t)(itb / NB) & 1u) ^ 1u);
+                            mbar_expect_tx(&b_full[sb], (uint32_t)B_BYTES);
+                            tma_load_2d(&tmW, sW + sb * B_BYTES, &b_full[sb], tap * a.nchunks * 32 + c * 32, 0);
+                        }
+                    }
                 }
             }
         }
     } else if (pw == 1) {
         if (lane == 0) {
             // ===== MMA issuer =====
-            mbar_wait(w_full, 0);
-            tcgen05_fence_after();
+            if (RES) { mbar_wait(w_full, 0); tcgen05_fence_after(); }
             const uint32_t w_base = smem_u32(sW);
-            int it = 0, tc = 0;
+            int it = 0, tc = 0, itb = 0;
             for (int t = t_first; t < a.n_tiles; t += t_step, ++tc) {
                 const int buf = tc & 1;
                 mbar_wait(&acc_empty[buf], ((uint32_t)(tc >> 1) & 1u) ^ 1u);
@@ -136,10 +152,21 @@ conv3_win_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const uint32_t a_tap = p_base + (uint32_t)(((tap / 3) * PW + (tap % 3)) * 128);
-                        const uint32_t b_tap = w_base + (uint32_t)((c * 9 + tap) * B_BYTES);
+                        uint32_t b_tap;
+                        int sb = 0;
+                        if (RES) {
+                            b_tap = w_base + (uint32_t)((c * 9 + tap) * B_BYTES);
+                        } else {
+                            sb = itb % NB;
+                            mbar_wait(&b_full[sb], (uint32_t)(itb / NB) & 1u);
+                            tcgen05_fence_after();
+                            b_tap = w_base + (uint32_t)(sb * B_BYTES);
+                            ++itb;
+                        }
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_tf32(d, make_smem_desc(a_tap + k * 32), make_smem_desc(b_tap + k * 32), IDESC, (c | tap | k) != 0 ? 1u : 0u);
+                        if (!RES) tcgen05_commit(&b_empty[sb]);
                     }
                     tcgen05_commit(&p_empty[s]);             // the patch may be overwritten once these MMAs have read it
                 }
@@ -249,22 +276,23 @@ int load_encoder() {
     return 0;
 }
 
-size_t win_smem_bytes(int nchunks, int BN) {
-    return (size_t)PIPES * PIPE_BYTES + (size_t)nchunks * 9 * BN * 128 + 256 + 1024;
+size_t win_smem_bytes(int nchunks, int BN, bool res) {
+    return (size_t)PIPES * PIPE_BYTES + (res ? (size_t)nchunks * 9 * BN * 128 : (size_t)PIPES * NB * BN * 128) + 512 + 1024;
 }
+bool win_resident(int nchunks, int BN) { return win_smem_bytes(nchunks, BN, true) <= 227 * 1024; }
 
-template <int BN>
+template <int BN, bool RES>
 int launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const WinArgs& a, cudaStream_t st) {
-    const size_t smem = win_smem_bytes(a.nchunks, BN);
-    SMK_REQUIRE(smem <= 227 * 1024, "conv3_win: weights do not fit next to the patch rings (%zu bytes)", smem);
+    const size_t smem = win_smem_bytes(a.nchunks, BN, RES);
+    SMK_REQUIRE(smem <= 227 * 1024, "conv3_win: shared-memory budget exceeded (%zu bytes)", smem);
     static unsigned long long configured_mask = 0;
     int dev = 0;
     SMK_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !(configured_mask & (1ull << dev))) {
-        SMK_CHECK_CUDA(cudaFuncSetAttribute(conv3_win_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SMK_CHECK_CUDA(cudaFuncSetAttribute((conv3_win_kernel<BN, RES>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         if (dev < 64) configured_mask |= 1ull << dev;
     }
-    SMK_LAUNCH((conv3_win_kernel<BN>), dim3((unsigned)std::min(cdiv(a.n_tiles, PIPES), 148)), dim3(NUM_THREADS), smem, st, tmX, tmW, a);
+    SMK_LAUNCH((conv3_win_kernel<BN, RES>), dim3((unsigned)std::min(cdiv(a.n_tiles, PIPES), 148)), dim3(NUM_THREADS), smem, st, tmX, tmW, a);
     SMK_CHECK_LAUNCH();
     return 0;
 }
@@ -276,13 +304,14 @@ bool conv3_win_supported(const TcConv& p) {
     if (!on || p.mode != 1 || p.res || p.wt_lo || (p.store != 0 && p.store != 3) || (p.store == 3 && p.N != 32)) return false;
     if (p.Cin % 32 != 0 || p.K != 9 * p.Cin || (p.N != 32 && p.N != 64)) return false;
     if (p.W < 56) return false;                                   // low-resolution layers are MMA-bound: gemm_tc's wide tiles win there
-    return win_smem_bytes(p.Cin / 32, p.N <= 32 ? 32 : 64) <= 227 * 1024;      // resident weights: 36 KB (32->32), 72 KB (64->32, 32->64)
+    static const int ring_on = []() { const char* e = getenv("SMK_CONV3_WIN_RING"); return e ? atoi(e) : 1; }();
+    return ring_on || win_resident(p.Cin / 32, p.N <= 32 ? 32 : 64);   // resident weights: 36 KB (32->32), 72 KB (64->32, 32->64); else a ring
 }
 
 // p uses TcConv semantics: mode 1 (3x3, zero padding 1), store 0 or 3, no residual.
 int conv3_win(const TcConv& p, cudaStream_t st) {
     if (int rc = load_encoder()) return rc;
-    SMK_REQUIRE(conv3_win_supported(p), "conv3_win: unsupported problem (needs 3x3 zero-pad, Cin %% 32 == 0, N in {32, 64}, W >= 56, resident weights)");
+    SMK_REQUIRE(conv3_win_supported(p), "conv3_win: unsupported problem (needs 3x3 zero-pad, Cin %% 32 == 0, N in {32, 64}, W >= 56)");
     SMK_REQUIRE(p.N % 4 == 0 && p.ld_in % 4 == 0 && p.ld_out % 4 == 0, "conv3_win: N and strides must be multiples of 4");
     SMK_REQUIRE(p.store != 3 || (p.N == 32 && p.head_w && p.head_b && p.head_c >= 1 && p.head_c <= 4), "conv3_win: the fused head needs N == 32");
     const int BN = p.N <= 32 ? 32 : 64;
@@ -316,7 +345,8 @@ int conv3_win(const TcConv& p, cudaStream_t st) {
         if (g_prof_detail) tag = prof_shape_tag(tag, (long)M, p.K, p.N);
         SMK_TAG(tag, 4.0 * (M * p.Cin + (double)p.K * p.N + M * (p.store == 3 ? p.head_c : p.N) + 2.0 * p.N), 2.0 * M * p.N * p.K, st);
     }
-    return BN == 32 ? launch<32>(tmX, tmW, a, st) : launch<64>(tmX, tmW, a, st);
+    if (win_resident(a.nchunks, BN)) return BN == 32 ? launch<32, true>(tmX, tmW, a, st) : launch<64, true>(tmX, tmW, a, st);
+    return BN == 32 ? launch<32, false>(tmX, tmW, a, st) : launch<64, false>(tmX, tmW, a, st);
 }
 
 }  // namespace smk

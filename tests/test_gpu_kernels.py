@@ -358,7 +358,8 @@ def test_conv3_win_exact_on_small_integers(native_lib):
     swizzled window, wrap columns, zero-filled halo), the resident-weight indexing, the tile decode and the split of the
     tiles over the two pipelines of a CTA."""
     g = torch.Generator().manual_seed(71)
-    for (B, H, W, Cin, N) in [(2, 61, 70, 32, 32), (1, 56, 56, 64, 32), (3, 57, 113, 32, 64), (1, 60, 56, 32, 32)]:
+    for (B, H, W, Cin, N) in [(2, 61, 70, 32, 32), (1, 56, 56, 64, 32), (3, 57, 113, 32, 64), (1, 60, 56, 32, 32),
+                              (1, 60, 64, 64, 64), (2, 57, 59, 128, 64)]:          # the last two stream their weights through the ring
         x = torch.randint(-3, 4, (B, Cin, H, W), generator=g).float()
         w = torch.randint(-2, 3, (N, Cin, 3, 3), generator=g).float()
         one, zero = torch.ones(N), torch.zeros(N)
@@ -368,7 +369,8 @@ def test_conv3_win_exact_on_small_integers(native_lib):
         assert torch.equal(got, ref), "B %d H %d W %d Cin %d N %d: %d mismatches" % (B, H, W, Cin, N, int((got != ref).sum()))
 
 
-@pytest.mark.parametrize("B,H,W,Cin,N", [(2, 224, 224, 32, 32), (1, 224, 224, 64, 32), (2, 112, 112, 32, 64), (5, 64, 90, 32, 32)])
+@pytest.mark.parametrize("B,H,W,Cin,N", [(2, 224, 224, 32, 32), (1, 224, 224, 64, 32), (2, 112, 112, 32, 64), (5, 64, 90, 32, 32),
+                                         (2, 112, 112, 64, 64), (1, 112, 112, 128, 64)])
 def test_conv3_win_random_with_epilogue(native_lib, B, H, W, Cin, N):
     x, w, scale, bias = make_case(B, H, W, Cin, N, 72, 1)
     for relu in (1, 0):
