@@ -322,7 +322,7 @@ def run_workload(cx, args, B, generator, slots, R, with_cpu):
 
     out = {"batch": B, "launches_per_step": int(rec["launches"])}
     faces = B * world * K
-    gather_keys = pipe.enable_gather(keys) if (world > 1 and not args.no_gather) else ()
+    gather_keys = pipe.enable_gather(keys, backend=args.gather_backend) if (world > 1 and not args.no_gather) else ()
     sampler = ClockSampler(cx.local)
     if rank == 0:
         sampler.start()
@@ -339,7 +339,9 @@ def run_workload(cx, args, B, generator, slots, R, with_cpu):
                   "host_checksum": float(cx.last["params"].double().abs().sum())}          # touches the host result
     if gather_keys:
         gb = pipe.gather_bytes_per_step(B)
-        out["gather"] = {"collective": "NCCL all_gather_into_tensor of %s per step, on a communication stream inside the timed region" % "+".join(gather_keys),
+        how = {"nccl": "NCCL all_gather_into_tensor", "p2p": "peer-to-peer pushes (CUDA IPC-mapped gather buffers, copy engines over NVLink)"}.get(pipe._gather_backend, str(pipe._gather_backend))
+        out["gather"] = {"backend": pipe._gather_backend,
+                         "collective": "%s of %s per step, on a communication stream inside the timed region" % (how, "+".join(gather_keys)),
                          "recv_bytes_per_rank_per_step": gb, "recv_gbs_per_rank": gb / (out["ms_per_step"] * 1e-3) / 1e9}
         pipe.enable_gather(())
         ms3 = timed_windows(cx, dev_step, pipe.join, K, W, max(3, R // 2))
@@ -450,6 +452,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="N > 1: leave the NCCL all-gather of the outputs out of the timed region")
+    ap.add_argument("--gather-backend", default="auto", choices=["auto", "nccl", "p2p"],
+                    help="N > 1: how the final outputs are all-gathered (auto: peer-to-peer copy-engine pushes if every rank can map its peers, else NCCL)")
     ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--slots", type=int, default=4, help="pipeline lanes: consecutive batches alternate over this many stream/graph replicas")
     ap.add_argument("--full-slots", type=int, default=2)
