@@ -202,12 +202,15 @@ class SmirkPipeline:
         """After every batch, all-gather the listed outputs over the process group (dim 0 = rank-major frames) on a
         communication stream; results land in ``gathered(i, key)``.  ``keys = ()`` switches it off.
 
-        backend "nccl": ``all_gather_into_tensor`` (NVLink 5 / NVSwitch; NCCL's kernels take SMs from the compute kernels
-        they overlap with: measured -4.7 % at 2 GPUs).  backend "p2p": every rank's gather buffers are mapped into all
-        ranks of the node (CUDA IPC) and each rank PUSHES its shard into its slice of every peer's buffer with
-        device-to-device copies on the communication stream — the copy engines move the bytes over NVLink, no SM is
-        involved.  A slot of a peer's buffer is rewritten ``slots`` batches later; ``gather_sync()`` (stream join + group
-        barrier) makes a batch's gathered tensors safe to read.  "auto": p2p if the mapping succeeds on every rank, else nccl."""
+        backend "nccl" (= "auto"): ``all_gather_into_tensor`` over NVLink 5 / NVSwitch; NCCL's kernels take SMs from the
+        compute kernels they overlap with: measured -4.7 % (B = 32) / -3.6 % (full cycle, B = 256) at 2 GPUs.
+        backend "p2p" (experimental): every rank's gather buffers are mapped into all ranks of the node (CUDA IPC) and
+        each rank PUSHES its shard into its slice of every peer's buffer with device-to-device copies on the communication
+        stream.  Results identical to NCCL (tools/check_gather.py), but torch's cross-device ``copy_`` serialises on the
+        peer device's stream and reached only 17 GB/s per rank at 21 MB per step: 26.1k instead of 65.6k faces/s at B = 32,
+        -5.7 % at B = 256 (profiles/r02_bench_n2_p2p_gather.json) — kept for the comparison, not the default.  A slot of a
+        peer's buffer is rewritten ``slots`` batches later; ``gather_sync()`` (stream join + group barrier) makes a batch's
+        gathered tensors safe to read."""
         import torch.distributed as dist
         self._gather_keys = tuple(keys) if (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1) else ()
         self._gather_group = group
@@ -215,7 +218,7 @@ class SmirkPipeline:
         if self._gather_keys:
             if self._comm is None:
                 self._comm = torch.cuda.Stream(device=self.device)
-            self._gather_backend = "nccl" if backend == "nccl" else "pending-" + backend
+            self._gather_backend = "pending-p2p" if backend == "p2p" else "nccl"
         return self._gather_keys
 
     def _setup_p2p(self, B):
