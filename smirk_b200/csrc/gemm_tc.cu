@@ -75,23 +75,23 @@ gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcArgs a) {
     //   PERSIST = false: grid = tiles, one tile per CTA, the epilogue staging slab aliases the (by then idle)
     //                    first ring stage and TMEM holds one accumulator: smaller footprint -> 3-5 CTAs per SM,
     //                    which is what the shallow-K streaming 1x1 layers want (more epilogue warps in flight).
-    //   X3 = true      : error-compensated "3xTF32" arithmetic (fp32-equivalent results on the tensor cores).  Every fp32
+    //   X3 = 2         : error-compensated "3xTF32" arithmetic (fp32-equivalent results on the tensor cores).  Every fp32
     //                    operand is split into a TF32 head and a TF32 tail, a = a_hi + a_lo, and three products are
     //                    accumulated: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (the dropped a_lo*w_lo term is ~2^-22 relative).
-    //                    Weights are split on the host (tmBlo maps the tails); the activation tile is split in shared
-    //                    memory by the epilogue warps, which are otherwise idle during the main loop of a single-tile
-    //                    CTA: they rewrite the landed A tile with its heads (so the tensor core sees exact TF32 words
-    //                    whatever it does with the low mantissa bits) and write the tails to a second tile.
-    //                    X3 = 1 keeps the tails in shared memory (stage = [A][B][A_lo][B_lo]); X3 = 2 parks them in TENSOR
-    //                    MEMORY instead (32 columns per stage next to the accumulator) and multiplies them with the
-    //                    A-from-TMEM form of tcgen05.mma: the shared-memory footprint stays that of the plain TF32 kernel
-    //                    plus the weight tails, so as many CTAs share an SM as before — which is what the concurrent
-    //                    pipeline's throughput hangs on (DESIGN.md "footprint beats per-kernel speed").
+    //                    Weights are split on the host (TcMaps::blo maps the tails).  The activation tile is split after TMA has
+    //                    landed it, by the epilogue warps — otherwise idle during the main loop of a single-tile CTA: thread =
+    //                    tile row = TMEM lane; the tails go to TENSOR MEMORY (32 columns per ring stage next to the
+    //                    accumulator) and are multiplied with the A-from-TMEM form of tcgen05.mma; the heads are what the
+    //                    tensor core reads from the fp32 words itself (it truncates to TF32; x3_trunc = 0 rewrites them in
+    //                    place, round to nearest).  The shared-memory footprint is that of the plain TF32 kernel plus the
+    //                    weight tails, so as many CTAs share an SM as before — which is what the concurrent pipeline's
+    //                    throughput hangs on (DESIGN.md "footprint beats per-kernel speed").  A first cut with the tails in a
+    //                    second shared-memory tile cost 10 % end to end (27.2k vs 30.2k faces/s) and was removed.
     static_assert(!X3 || !PERSIST, "the 3xTF32 split borrows the epilogue warps: single-tile CTAs only");
     constexpr int B_STAGE_BYTES = BN * BKB;
     constexpr int HALF_STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    constexpr int STAGE_BYTES = X3 == 1 ? 2 * HALF_STAGE_BYTES : (X3 == 2 ? HALF_STAGE_BYTES + B_STAGE_BYTES : HALF_STAGE_BYTES);
-    constexpr int BLO_OFF = X3 == 1 ? HALF_STAGE_BYTES + A_STAGE_BYTES : HALF_STAGE_BYTES;      // weight tails within a stage
+    constexpr int STAGE_BYTES = X3 ? HALF_STAGE_BYTES + B_STAGE_BYTES : HALF_STAGE_BYTES;         // [A][B] (+ [B tails])
+    constexpr int BLO_OFF = HALF_STAGE_BYTES;                                                       // weight tails within a stage
     constexpr uint32_t ALO_COL = PERSIST ? 2 * BN : BN;                                            // X3 == 2: first TMEM column of the A tails
     constexpr uint32_t TMEM_NEED = (PERSIST ? 2 * BN : BN) + (X3 == 2 ? STAGES * 32 : 0);
     constexpr uint32_t TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
@@ -179,8 +179,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcArgs a) {
                         umma_tf32(tmem_base + (uint32_t)(buf * BN), da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
                         if (X3) {
                             uint64_t dbl = make_smem_desc(sa + BLO_OFF + k * UMMA_K * 4);
-                            if (X3 == 1) umma_tf32(tmem_base + (uint32_t)(buf * BN), make_smem_desc(sa + HALF_STAGE_BYTES + k * UMMA_K * 4), db, IDESC, 1u);   // a_lo * w_hi
-                            else umma_tf32_ts(tmem_base + (uint32_t)(buf * BN), tmem_base + ALO_COL + (uint32_t)(s * 32 + k * UMMA_K), db, IDESC, 1u);
+                            umma_tf32_ts(tmem_base + (uint32_t)(buf * BN), tmem_base + ALO_COL + (uint32_t)(s * 32 + k * UMMA_K), db, IDESC, 1u);
                             umma_tf32(tmem_base + (uint32_t)(buf * BN), da, dbl, IDESC, 1u);      // a_hi * w_lo
                         }
                     }
@@ -232,26 +231,6 @@ gemm_tc_kernel(const __grid_constant__ TcMaps mp, const TcArgs a) {
                 if (lane == 0) mbar_arrive(&split[s]);
             }
             tcgen05_fence_after();
-        } else if (X3 == 1) {
-            // ===== 3xTF32: split every landed A tile into TF32 heads (in place) and tails (second tile) =====
-            const int t = threadIdx.x - 64;                        // 0..127
-            for (int kb = 0; kb < a.nkb; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(&full[s], (uint32_t)(kb / STAGES) & 1u);
-                float4* A = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
-                float4* AL = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + HALF_STAGE_BYTES);
-#pragma unroll
-                for (int j = 0; j < A_STAGE_BYTES / 16 / 128; ++j) {
-                    const float4 v = A[t + 128 * j];
-                    float4 hi, lo;
-                    hi.x = smk::round_tf32(v.x); hi.y = smk::round_tf32(v.y); hi.z = smk::round_tf32(v.z); hi.w = smk::round_tf32(v.w);
-                    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;       // exact
-                    A[t + 128 * j] = hi; AL[t + 128 * j] = lo;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&split[s]);
-            }
         }
         uint8_t* slab = slabs + quarter * 4096;
         const int sub = lane >> 3, jj = lane & 7;              // phase-2 role: row-in-group, 16-byte chunk
@@ -444,7 +423,7 @@ int encode_im2col(CUtensorMap* map, const float* base, int B, int Hin, int Win, 
 
 template <int BN, int STAGES, int MINB, bool PERSIST, int X3 = 0>
 int launch(const TcMaps& mp, const TcArgs& a_in, cudaStream_t st, int groups) {
-    constexpr size_t stage = X3 == 1 ? 2 * (A_STAGE_BYTES + BN * BKB) : (X3 == 2 ? A_STAGE_BYTES + 2 * BN * BKB : A_STAGE_BYTES + BN * BKB);
+    constexpr size_t stage = X3 ? A_STAGE_BYTES + 2 * BN * BKB : A_STAGE_BYTES + BN * BKB;
     constexpr size_t smem = (size_t)STAGES * stage + (PERSIST ? SLAB_BYTES : 0) + 1024 + 256;
     static_assert(MINB * (smem + 1024) <= 228 * 1024, "shared memory budget of MINB resident CTAs");
     static_assert(MINB * ((PERSIST ? 2 : 1) * BN + (X3 == 2 ? STAGES * 32 : 0)) <= 512, "TMEM budget of MINB resident CTAs");
@@ -545,25 +524,18 @@ int tc_conv(const TcConv& p, cudaStream_t st, const TcConv* p2) {
                 groups * 2.0 * (double)M * p.N * p.K, st);
     }
     if (p.wt_lo) {                                      // 3xTF32: fp32-equivalent arithmetic (encoder precision 3)
-        // tails of the activations in tensor memory (default) or in shared memory (SMK_X3_TMEM=0: the first, larger-footprint cut)
-        static const int x3_tmem = []() { const char* e = getenv("SMK_X3_TMEM"); return e ? atoi(e) : 1; }();
         // deep-K layers (the 14x14 / 7x7 projections, K = 480..960): per k-block the chain TMA -> split -> MMA -> free is
         // ~1.5 us with a 2-stage ring (measured: 47 us for K = 960); a 4-stage ring keeps three loads in flight and is
         // faster alone, but its footprint costs the concurrent pipeline 3 % (29.8k vs 30.6k faces/s): opt-in, SMK_X3_DEEP=1
         static const int x3_deep = []() { const char* e = getenv("SMK_X3_DEEP"); return e ? atoi(e) : 0; }();
-        if (x3_tmem && x3_deep && a.nkb >= 8) {
+        if (x3_deep && a.nkb >= 8) {
             if (BN == 32) return launch<32, 4, 2, false, 2>(mp, a, st, groups);
             if (BN == 64) return launch<64, 4, 1, false, 2>(mp, a, st, groups);
             return launch<128, 4, 1, false, 2>(mp, a, st, groups);
         }
-        if (x3_tmem) {
-            if (BN == 32) return launch<32, 2, 4, false, 2>(mp, a, st, groups);
-            if (BN == 64) return launch<64, 2, 3, false, 2>(mp, a, st, groups);
-            return launch<128, 2, 2, false, 2>(mp, a, st, groups);
-        }
-        if (BN == 32) return launch<32, 2, 2, false, 1>(mp, a, st, groups);
-        if (BN == 64) return launch<64, 2, 2, false, 1>(mp, a, st, groups);
-        return launch<128, 2, 1, false, 1>(mp, a, st, groups);
+        if (BN == 32) return launch<32, 2, 4, false, 2>(mp, a, st, groups);
+        if (BN == 64) return launch<64, 2, 3, false, 2>(mp, a, st, groups);
+        return launch<128, 2, 2, false, 2>(mp, a, st, groups);
     }
     if (deep_small && BN == 32) return launch<32, 8, 1, false>(mp, a, st, groups);
     if (deep_small && BN == 64) return launch<64, 8, 1, false>(mp, a, st, groups);

@@ -68,22 +68,24 @@ struct XdwArgs {
     int x3_trunc;                  // see gemm_tc.cu: 1 = the tensor core's own truncation of fp32 words is the head
 };
 
-// X3 = true: error-compensated 3xTF32 expand GEMM (fp32-equivalent e): x = x_hi + x_lo split in shared memory by four
-// dedicated warps (heads rewritten in place, tails in a second window), w1 = w_hi + w_lo split on the host (tmWlo);
-// e = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo accumulated in the same TMEM columns.  One CTA per SM (184 KB of shared memory).
-// X3 = 2: the tails of x live in TENSOR MEMORY (64 more columns per ring stage) instead of a second shared-memory window and
-// are multiplied with the A-from-TMEM form of tcgen05.mma — shared memory stays at the plain kernel's 113 KB + the weight
-// tails, so the SM keeps room for the other kernels of the concurrent pipeline.
+// X3 != 0: error-compensated 3xTF32 expand GEMM (fp32-equivalent e): x = x_hi + x_lo, w1 = w_hi + w_lo (split on the host, tmWlo),
+// e = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo accumulated in the same TMEM columns.  The tails of x live in TENSOR MEMORY (64 columns
+// per ring stage next to the accumulators) and are multiplied with the A-from-TMEM form of tcgen05.mma, so shared memory stays
+// at the plain kernel's 113 KB + the weight tails.  Who splits the landed x window:
+//   X3 = 3  the eight WORKER warps, at the top of chunk c for the stages of chunk c + 1 (thread = one window row of its warp's
+//           TMEM lane quarter): 320 threads like the plain kernel, so the SM keeps registers for the concurrent kernels.
+//           Needs every k-block of a chunk resident at once: Cin <= 32 * STAGES.
+//   X3 = 2  four dedicated splitter warps (448 threads): any Cin.
 template <int STRIDE, int X3>
-__global__ void __launch_bounds__(NUM_THREADS + (X3 ? NUM_SPLITTERS : 0), X3 ? 1 : 2) __maxnreg__(X3 ? 96 : 102)
+__global__ void __launch_bounds__(NUM_THREADS + (X3 == 2 ? NUM_SPLITTERS : 0), X3 ? 1 : 2) __maxnreg__(X3 == 2 ? 96 : 102)
 xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
     constexpr int TO = STRIDE == 1 ? 14 : 7;                    // output tile edge
-    constexpr int STAGE_BYTES = X3 == 1 ? 2 * smk::STAGE_BYTES : (X3 == 2 ? smk::STAGE_BYTES + B_BYTES : smk::STAGE_BYTES);
-    constexpr int LO = smk::STAGE_BYTES;                        // X3 == 1: offset of the tails ([x half 0][x half 1][w] again) within a stage
-    constexpr int WLO = X3 == 1 ? LO + 2 * HALF_BYTES : smk::STAGE_BYTES;   // offset of the weight tails
-    constexpr uint32_t XLO_COL = smk::TMEM_COLS;                // X3 == 2: first TMEM column of the x tails (stage s, half h -> + (2 s + h) * 32)
-    constexpr uint32_t TMEM_COLS = X3 == 2 ? 256u : smk::TMEM_COLS;
-    static_assert(X3 != 2 || 128 + STAGES * 64 <= 256, "TMEM columns");
+    constexpr int STAGE_BYTES = X3 ? smk::STAGE_BYTES + B_BYTES : smk::STAGE_BYTES;      // [x half 0][x half 1][w] (+ [w tails])
+    constexpr int WLO = smk::STAGE_BYTES;                       // offset of the weight tails within a stage
+    constexpr uint32_t XLO_COL = smk::TMEM_COLS;                // first TMEM column of the x tails (stage s, half h -> + (2 s + h) * 32)
+    constexpr uint32_t TMEM_COLS = X3 ? 256u : smk::TMEM_COLS;
+    constexpr int SPLIT_ARRIVALS = X3 == 3 ? NUM_WORKERS / 32 : NUM_SPLITTERS / 32;
+    static_assert(!X3 || 128 + STAGES * 64 <= 256, "TMEM columns");
     constexpr uint32_t IDESC = make_idesc(128, NC);
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B; offset arithmetic (not an integer round-trip of the pointer) keeps
@@ -95,7 +97,7 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
     uint64_t* empty = full + STAGES;
     uint64_t* acc_full = empty + STAGES;
     uint64_t* acc_empty = acc_full + 2;
-    uint64_t* split = acc_empty + 2;                            // X3: stage s has been split (4 splitter warps arrive)
+    uint64_t* split = acc_empty + 2;                            // X3: stage s has been split (one arrival per splitting warp)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(split + STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,7 +121,7 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mp.x[0]) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mp.w[0]) : "memory");
         if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&mp.wlo[0]) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&split[s], NUM_SPLITTERS / 32); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&split[s], SPLIT_ARRIVALS); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NUM_WORKERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -132,6 +134,34 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_sync();
+
+    // 3xTF32: split 32 rows x 32 channels of one half of the x window in stage s — thread = window row r of its warp's TMEM lane
+    // quarter (a warp may only touch lanes [32 * (warp % 4), +32)).  Tails -> tensor memory; heads either implicit (the tensor core
+    // truncates fp32 words to TF32: x3_trunc) or rewritten in place (round to nearest).
+    auto split_rows = [&](int s, int half) {
+        const int r = (warp & 3) * 32 + lane;
+        uint8_t* row = smem + s * STAGE_BYTES + half * HALF_BYTES + r * 128;
+        float lo[32];
+        if (a.x3_trunc) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 v = *reinterpret_cast<const float4*>(row + ((j ^ (r & 7)) << 4));
+                lo[4 * j] = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo[4 * j + 1] = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                lo[4 * j + 2] = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo[4 * j + 3] = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4* p = reinterpret_cast<float4*>(row + ((j ^ (r & 7)) << 4));
+                const float4 v = *p;
+                float4 hi;
+                hi.x = round_tf32(v.x); hi.y = round_tf32(v.y); hi.z = round_tf32(v.z); hi.w = round_tf32(v.w);
+                lo[4 * j] = v.x - hi.x; lo[4 * j + 1] = v.y - hi.y; lo[4 * j + 2] = v.z - hi.z; lo[4 * j + 3] = v.w - hi.w;
+                *p = hi;
+            }
+        }
+        tmem_st32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + XLO_COL + (uint32_t)((s * 2 + half) * 32), lo);
+    };
 
     if (warp == 0) {
         if (lane == 0) {
@@ -178,9 +208,8 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
                             const uint64_t db = make_smem_desc(sb + k * UMMA_K * 4);
                             umma_tf32(d, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
                             if (X3) {
-                                if (X3 == 1) umma_tf32(d, make_smem_desc(sa + LO + half * HALF_BYTES + k * UMMA_K * 4), db, IDESC, 1u);   // x_lo * w_hi
-                                else umma_tf32_ts(d, tmem_base + XLO_COL + (uint32_t)((s * 2 + half) * 32 + k * UMMA_K), db, IDESC, 1u);
-                                umma_tf32(d, da, make_smem_desc(sa + WLO + k * UMMA_K * 4), IDESC, 1u);                      // x_hi * w_lo
+                                umma_tf32_ts(d, tmem_base + XLO_COL + (uint32_t)((s * 2 + half) * 32 + k * UMMA_K), db, IDESC, 1u);   // x_lo * w_hi
+                                umma_tf32(d, da, make_smem_desc(sa + WLO + k * UMMA_K * 4), IDESC, 1u);                               // x_hi * w_lo
                             }
                         }
                     tcgen05_commit(&empty[s]);
@@ -189,9 +218,8 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
               }
             }
         }
-    } else if (X3 && warp >= 2 + NUM_WORKERS / 32) {
-        // ===== splitters (3xTF32): x window -> TF32 heads in place + tails, one ring stage at a time =====
-        const int t = threadIdx.x - (64 + NUM_WORKERS);    // 0..127
+    } else if (X3 == 2 && warp >= 2 + NUM_WORKERS / 32) {
+        // ===== dedicated splitters: both halves of every landed x window, one ring stage at a time =====
         int it = 0;
         for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
             const Item w = decode(item);
@@ -199,49 +227,9 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
                 for (int kb = 0; kb < a.nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
-                    if (X3 == 2) {
-                        // thread = window row r of each half = its TMEM lane (a warp may only touch lane quarter warp % 4):
-                        // heads rewritten in place, tails -> tensor memory
-                        const int r = (warp & 3) * 32 + lane;
-#pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            uint8_t* row = smem + s * STAGE_BYTES + half * HALF_BYTES + r * 128;
-                            float lo[32];
-                            if (a.x3_trunc) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float4 v = *reinterpret_cast<const float4*>(row + ((j ^ (r & 7)) << 4));
-                                    lo[4 * j] = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo[4 * j + 1] = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                                    lo[4 * j + 2] = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo[4 * j + 3] = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    float4* p = reinterpret_cast<float4*>(row + ((j ^ (r & 7)) << 4));
-                                    const float4 v = *p;
-                                    float4 hi;
-                                    hi.x = round_tf32(v.x); hi.y = round_tf32(v.y); hi.z = round_tf32(v.z); hi.w = round_tf32(v.w);
-                                    lo[4 * j] = v.x - hi.x; lo[4 * j + 1] = v.y - hi.y; lo[4 * j + 2] = v.z - hi.z; lo[4 * j + 3] = v.w - hi.w;
-                                    *p = hi;
-                                }
-                            }
-                            tmem_st32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + XLO_COL + (uint32_t)((s * 2 + half) * 32), lo);
-                        }
-                        if (!a.x3_trunc) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        tcgen05_fence_before();
-                    } else {
-                        float4* X = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
-                        float4* XL = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + LO);
-#pragma unroll 4
-                        for (int j = 0; j < 2 * HALF_BYTES / 16 / NUM_SPLITTERS; ++j) {
-                            const float4 v = X[t + NUM_SPLITTERS * j];
-                            float4 hi, lo;
-                            hi.x = round_tf32(v.x); hi.y = round_tf32(v.y); hi.z = round_tf32(v.z); hi.w = round_tf32(v.w);
-                            lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;       // exact
-                            X[t + NUM_SPLITTERS * j] = hi; XL[t + NUM_SPLITTERS * j] = lo;
-                        }
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    }
+                    split_rows(s, 0); split_rows(s, 1);
+                    if (!a.x3_trunc) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&split[s]);
                 }
@@ -276,6 +264,25 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
         };
         if ((int)blockIdx.x < a.n_items) { const Item w0 = decode(blockIdx.x); park_par(0, load_par(w0.prob, w0.c_begin)); }
         worker_barrier();
+        // X3 == 3: the workers split the x windows themselves.  Chunk k of this CTA's sequence owns ring iterations
+        // [k * nkb, (k + 1) * nkb); at the top of chunk cc the stages of chunk cc + 1 have landed long ago (they were freed when
+        // the MMAs of chunk cc, issued one iteration earlier, completed), so the split costs ~0.2 us per chunk and the MMAs of
+        // chunk cc + 1 still overlap phases (a)/(b) of chunk cc.  Worker warp (half, quarter) owns rows [32 * quarter, +32) of `half`.
+        int total_chunks = 0;
+        if (X3 == 3)
+            for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) { const Item wi = decode(item); total_chunks += wi.c_end - wi.c_begin; }
+        auto split_chunk = [&](int k) {
+            for (int kb = 0; kb < a.nkb; ++kb) {
+                const int it = k * a.nkb + kb, s = it % STAGES;
+                mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
+                split_rows(s, half);
+                if (!a.x3_trunc) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&split[s]);
+            }
+        };
+        if (X3 == 3 && total_chunks > 0) split_chunk(0);
         int cc = 0;
         for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
           const Item w = decode(item);
@@ -296,6 +303,7 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
             const int c_next = c + 1 < w.c_end ? c + 1 : next_first;
             float2 pf = make_float2(0.f, 0.f);
             if (c_next >= 0) pf = load_par(c + 1 < w.c_end ? w.prob : next_prob, c_next);
+            if (X3 == 3 && cc + 1 < total_chunks) split_chunk(cc + 1);
             mbar_wait(&acc_full[buf], (uint32_t)(cc >> 1) & 1u);
             tcgen05_fence_after();
             // (a) TMEM -> BN1 + ReLU -> E   (rows = window pixels, lane = pixel).  Channels past `mid` have zero
@@ -485,18 +493,16 @@ int xdw_conv(const XdwConv& p, cudaStream_t st, const XdwConv* p2) {
         a.x3_trunc = x3_trunc;
     }
     constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + E_BYTES + PAR_BYTES + 1024 + 256;
-    constexpr size_t smem3 = (size_t)STAGES * 2 * STAGE_BYTES + E_BYTES + PAR_BYTES + 1024 + 256;          // tails in shared memory
-    constexpr size_t smem3t = (size_t)STAGES * (STAGE_BYTES + B_BYTES) + E_BYTES + PAR_BYTES + 1024 + 256;  // tails in tensor memory
+    constexpr size_t smem3t = (size_t)STAGES * (STAGE_BYTES + B_BYTES) + E_BYTES + PAR_BYTES + 1024 + 256;  // 3xTF32: + the weight tails
     static_assert(2 * (smem + 1024) <= 228 * 1024, "two CTAs per SM");
-    static_assert(smem3 + 1024 <= 227 * 1024, "3xTF32 variant: one CTA per SM");
     static unsigned long long configured_mask = 0;       // per-device attribute, see gemm_tc.cu
     int dev = 0;
     SMK_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !(configured_mask & (1ull << dev))) {
         SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3t));
+        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3t));
         SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3t));
         SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3t));
         if (dev < 64) configured_mask |= 1ull << dev;
@@ -510,13 +516,14 @@ int xdw_conv(const XdwConv& p, cudaStream_t st, const XdwConv* p2) {
     a.n_items_p = a.tiles_x * a.tiles_y * p.B * a.groups;
     a.n_items = nprob * a.n_items_p;
     dim3 grid((unsigned)std::min(a.n_items, p.w1t_lo ? std::min(slots, 148) : slots));            // persistent: (up to) 2 CTAs per SM
-    static const int x3_tmem = []() { const char* e = getenv("SMK_X3_TMEM"); return e ? atoi(e) : 1; }();
-    if (p.w1t_lo && x3_tmem) {
+    // who splits: the worker warps when a chunk's k-blocks fit the ring (Cin <= 64: the 112^2 ... 28^2 blocks), else dedicated warps
+    static const int worker_split = []() { const char* e = getenv("SMK_XDW_WORKER_SPLIT"); return e ? atoi(e) : 1; }();
+    if (p.w1t_lo && worker_split && a.nkb <= STAGES) {
+        if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, 3>), dim3(grid), dim3(NUM_THREADS), smem3t, st, mp, a);
+        else SMK_LAUNCH((xdw_kernel<2, 3>), dim3(grid), dim3(NUM_THREADS), smem3t, st, mp, a);
+    } else if (p.w1t_lo) {
         if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, 2>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3t, st, mp, a);
         else SMK_LAUNCH((xdw_kernel<2, 2>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3t, st, mp, a);
-    } else if (p.w1t_lo) {
-        if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, 1>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3, st, mp, a);
-        else SMK_LAUNCH((xdw_kernel<2, 1>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3, st, mp, a);
     } else {
         if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, 0>), dim3(grid), dim3(NUM_THREADS), smem, st, mp, a);
         else SMK_LAUNCH((xdw_kernel<2, 0>), dim3(grid), dim3(NUM_THREADS), smem, st, mp, a);
