@@ -16,11 +16,11 @@ import json
 import re
 
 TAGS = [
-    (r"xdw_kernel<\d+, *[12]>", "xdw_fused_tc3x"), (r"xdw_kernel", "xdw_fused_tc"),
+    (r"xdw_kernel<\d+, *[123]>", "xdw_fused_tc3x"), (r"xdw_kernel", "xdw_fused_tc"),
     (r"gemm_tc_kernel<\d+, *\d+, *\d+, *(false|0), *[12]>", "pw_gemm_tc3x"),            # 3xTF32 variants (single-tile CTAs)
     (r"gemm_tc_kernel<\d+, *\d+, *\d+, *(true|1), *0>", "conv3x3_gemm_tc"),             # persistent CTAs: the generator's 3x3 convolutions
     (r"gemm_tc_kernel", "pw_gemm_tc"),                                                  # 1x1 convs / transposed convs
-    (r"gap_head_kernel", "gap_head"), (r"mask_\w+_kernel", "masking"),
+    (r"conv3_win_kernel", "conv3x3_win_tc"), (r"gap_head_kernel", "gap_head"), (r"mask_\w+_kernel", "masking"),
     (r"stem_ds_kernel", "stem_ds_fused"), (r"stem_conv3_kernel", "stem_conv3"), (r"stem_conv_kernel", "stem_conv"),
     (r"dwconv3x3", "dwconv3x3"), (r"conv_gemm_kernel", "conv_gemm_f32"), (r"raster_tile_kernel", "raster_tile"),
     (r"flame_verts_kernel", "flame_verts"), (r"flame_pose_kernel", "flame_pose"), (r"flame_landmarks_kernel", "flame_landmarks"),

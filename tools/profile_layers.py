@@ -42,10 +42,15 @@ def main():
         gen.load_state_dict(synth_inputs.random_state_dict(gen.state_dict(), seed=7))
         gen = gen.eval().to(dev)
         gen.precision = min(enc.precision, 1)
-    pipe = SmirkPipeline(enc, smirk_b200.FLAME().to(dev), smirk_b200.Renderer().to(dev), gen, device=dev)
+    fl = smirk_b200.FLAME().to(dev)
+    stage = None
+    if gen is not None:                     # the real masking step between renderer and generator, as in bench.py
+        from smirk_b200.masking import MaskingStage
+        stage = MaskingStage(fl.faces_tensor, synth_inputs.face_probabilities(fl.faces_tensor.shape[0]), seed=1234)
+    pipe = SmirkPipeline(enc, fl, smirk_b200.Renderer().to(dev), gen, device=dev, masking=stage)
     B = args.batch
     imgs = [synth_inputs.images(B, 100 + i).to(dev) for i in range(4)]
-    masks = [synth_inputs.masked_images(B, 200 + i).to(dev) for i in range(4)] if gen is not None else None
+    masks = [synth_inputs.hull_masks(B, 200 + i).to(dev) for i in range(4)] if gen is not None else None
     L = _lib.lib()
     for i in range(3):
         pipe.forward(imgs[i % 4], masks[i % 4] if masks else None)
