@@ -71,20 +71,18 @@ struct XdwArgs {
 // X3 != 0: error-compensated 3xTF32 expand GEMM (fp32-equivalent e): x = x_hi + x_lo, w1 = w_hi + w_lo (split on the host, tmWlo),
 // e = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo accumulated in the same TMEM columns.  The tails of x live in TENSOR MEMORY (64 columns
 // per ring stage next to the accumulators) and are multiplied with the A-from-TMEM form of tcgen05.mma, so shared memory stays
-// at the plain kernel's 113 KB + the weight tails.  Who splits the landed x window:
-//   X3 = 3  the eight WORKER warps, at the top of chunk c for the stages of chunk c + 1 (thread = one window row of its warp's
-//           TMEM lane quarter): 320 threads like the plain kernel, so the SM keeps registers for the concurrent kernels.
-//           Needs every k-block of a chunk resident at once: Cin <= 32 * STAGES.
-//   X3 = 2  four dedicated splitter warps (448 threads): any Cin.
+// at the plain kernel's 113 KB + the weight tails.  Four dedicated splitter warps (448 threads) split each landed x window;
+// letting the eight worker warps do it instead (320 threads, tried for Cin <= 64) measured 2 % slower end to end and 6-8 % slower
+// per layer (profiles/r02_xdw_worker_split_ab.txt), so that variant is gone.
 template <int STRIDE, int X3>
-__global__ void __launch_bounds__(NUM_THREADS + (X3 == 2 ? NUM_SPLITTERS : 0), X3 ? 1 : 2) __maxnreg__(X3 == 2 ? 96 : 102)
+__global__ void __launch_bounds__(NUM_THREADS + (X3 ? NUM_SPLITTERS : 0), X3 ? 1 : 2) __maxnreg__(X3 ? 96 : 102)
 xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
     constexpr int TO = STRIDE == 1 ? 14 : 7;                    // output tile edge
     constexpr int STAGE_BYTES = X3 ? smk::STAGE_BYTES + B_BYTES : smk::STAGE_BYTES;      // [x half 0][x half 1][w] (+ [w tails])
     constexpr int WLO = smk::STAGE_BYTES;                       // offset of the weight tails within a stage
     constexpr uint32_t XLO_COL = smk::TMEM_COLS;                // first TMEM column of the x tails (stage s, half h -> + (2 s + h) * 32)
     constexpr uint32_t TMEM_COLS = X3 ? 256u : smk::TMEM_COLS;
-    constexpr int SPLIT_ARRIVALS = X3 == 3 ? NUM_WORKERS / 32 : NUM_SPLITTERS / 32;
+    constexpr int SPLIT_ARRIVALS = NUM_SPLITTERS / 32;
     static_assert(!X3 || 128 + STAGES * 64 <= 256, "TMEM columns");
     constexpr uint32_t IDESC = make_idesc(128, NC);
     extern __shared__ uint8_t smem_raw[];
@@ -218,7 +216,7 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
               }
             }
         }
-    } else if (X3 == 2 && warp >= 2 + NUM_WORKERS / 32) {
+    } else if (X3 && warp >= 2 + NUM_WORKERS / 32) {
         // ===== dedicated splitters: both halves of every landed x window, one ring stage at a time =====
         int it = 0;
         for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
@@ -264,25 +262,6 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
         };
         if ((int)blockIdx.x < a.n_items) { const Item w0 = decode(blockIdx.x); park_par(0, load_par(w0.prob, w0.c_begin)); }
         worker_barrier();
-        // X3 == 3: the workers split the x windows themselves.  Chunk k of this CTA's sequence owns ring iterations
-        // [k * nkb, (k + 1) * nkb); at the top of chunk cc the stages of chunk cc + 1 have landed long ago (they were freed when
-        // the MMAs of chunk cc, issued one iteration earlier, completed), so the split costs ~0.2 us per chunk and the MMAs of
-        // chunk cc + 1 still overlap phases (a)/(b) of chunk cc.  Worker warp (half, quarter) owns rows [32 * quarter, +32) of `half`.
-        int total_chunks = 0;
-        if (X3 == 3)
-            for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) { const Item wi = decode(item); total_chunks += wi.c_end - wi.c_begin; }
-        auto split_chunk = [&](int k) {
-            for (int kb = 0; kb < a.nkb; ++kb) {
-                const int it = k * a.nkb + kb, s = it % STAGES;
-                mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
-                split_rows(s, half);
-                if (!a.x3_trunc) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&split[s]);
-            }
-        };
-        if (X3 == 3 && total_chunks > 0) split_chunk(0);
         int cc = 0;
         for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
           const Item w = decode(item);
@@ -303,7 +282,6 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
             const int c_next = c + 1 < w.c_end ? c + 1 : next_first;
             float2 pf = make_float2(0.f, 0.f);
             if (c_next >= 0) pf = load_par(c + 1 < w.c_end ? w.prob : next_prob, c_next);
-            if (X3 == 3 && cc + 1 < total_chunks) split_chunk(cc + 1);
             mbar_wait(&acc_full[buf], (uint32_t)(cc >> 1) & 1u);
             tcgen05_fence_after();
             // (a) TMEM -> BN1 + ReLU -> E   (rows = window pixels, lane = pixel).  Channels past `mid` have zero
@@ -501,8 +479,6 @@ int xdw_conv(const XdwConv& p, cudaStream_t st, const XdwConv* p2) {
     if (dev >= 64 || !(configured_mask & (1ull << dev))) {
         SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3t));
-        SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3t));
         SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3t));
         SMK_CHECK_CUDA(cudaFuncSetAttribute(xdw_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3t));
         if (dev < 64) configured_mask |= 1ull << dev;
@@ -516,12 +492,7 @@ int xdw_conv(const XdwConv& p, cudaStream_t st, const XdwConv* p2) {
     a.n_items_p = a.tiles_x * a.tiles_y * p.B * a.groups;
     a.n_items = nprob * a.n_items_p;
     dim3 grid((unsigned)std::min(a.n_items, p.w1t_lo ? std::min(slots, 148) : slots));            // persistent: (up to) 2 CTAs per SM
-    // who splits: the worker warps when a chunk's k-blocks fit the ring (Cin <= 64: the 112^2 ... 28^2 blocks), else dedicated warps
-    static const int worker_split = []() { const char* e = getenv("SMK_XDW_WORKER_SPLIT"); return e ? atoi(e) : 1; }();
-    if (p.w1t_lo && worker_split && a.nkb <= STAGES) {
-        if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, 3>), dim3(grid), dim3(NUM_THREADS), smem3t, st, mp, a);
-        else SMK_LAUNCH((xdw_kernel<2, 3>), dim3(grid), dim3(NUM_THREADS), smem3t, st, mp, a);
-    } else if (p.w1t_lo) {
+    if (p.w1t_lo) {
         if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, 2>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3t, st, mp, a);
         else SMK_LAUNCH((xdw_kernel<2, 2>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3t, st, mp, a);
     } else {

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--only", default="")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--x3", action="store_true", help="the 3xTF32 variant (smk_debug_xdw3x: weights split into TF32 heads and tails)")
     a = ap.parse_args()
     lib = _lib.lib()
     dev = torch.device("cuda:0")
@@ -52,7 +53,14 @@ def main():
         s2, b2 = torch.rand(mid, device=dev) + 0.5, torch.randn(mid, device=dev) * 0.2
         out = torch.empty(B, Ho, Ho, mid, device=dev)
 
+        w1_hi = (w1.view(torch.int32) & -8192).view(torch.float32)
+        w1_lo = w1 - w1_hi
+
         def run():
+            if a.x3:
+                rc = lib.smk_debug_xdw3x(P(x), B, H, H, Cin, P(w1_hi), P(w1_lo), P(s1), P(b1), mid, P(wd), P(s2), P(b2), stride, P(out), st)
+                assert rc == 0, lib.smk_last_error()
+                return
             rc = lib.smk_debug_xdw(P(x), B, H, H, Cin, P(w1), P(s1), P(b1), mid, P(wd), P(s2), P(b2), stride, 1, P(out), st)
             assert rc == 0, lib.smk_last_error()
 
