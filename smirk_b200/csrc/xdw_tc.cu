@@ -57,7 +57,9 @@ struct XdwArgs {
     int H, W, Ho, Wo;              // e (= x) resolution and output resolution
     int mid, nkb, nchunks;         // expanded channels, 32-wide k-blocks of Cin, 32-wide channel chunks
     int groups, chunks_per_group;  // a group owns chunks [g*cpg, min((g+1)*cpg, nchunks)); item = ((img*tiles_y + ty)*tiles_x + tx)*groups + g
-    int n_items, n_items_p;        // n_items_p: items per problem (two identically shaped problems may share one launch, like gemm_tc.cu)
+    int n_items, B;                // items of the launch (two identically shaped problems may share one, like gemm_tc.cu: image index B.. = problem 1)
+    int d_grp, d_tx, d_ty, d_img;  // (group, tile x, tile y, image) digits of the grid size: the item stride of a persistent CTA
+    unsigned geom;                 // depthwise row grouping for [columns full|edge][rows full|edge] tiles: byte = rows per thread | row groups << 4
     int pad;                       // TF-SAME pad_begin of the depthwise conv (1 for stride 1, 0 for stride 2 on even sizes)
     int tiles_x, tiles_y;          // output tiles per image
     const float* scale1[2]; const float* bias1[2];  // folded BN of the 1x1 conv        [mid]   (per problem)
@@ -103,15 +105,29 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
     // All three roles walk the same item sequence; the smem ring and the TMEM double buffer run across
     // item boundaries, so the x window / weights of item i+1 are in flight (and multiplied) while the
     // workers are still busy with item i.
+    // The item sequence of a CTA advances by gridDim.x; the (group, tile x, tile y, image) digits of the item index are
+    // carried along incrementally — one runtime decomposition per thread at kernel start instead of four integer divisions per
+    // item (which cost the workers ~16 % of their time on the two-chunk 112^2 block, profiles/r02_ncu_full_xdw3x_*.txt).
     struct Item { int prob, img, oh0, ow0, c_begin, c_end; };
-    auto decode = [&](int item) {
+    struct ItemIter { int item, grp, tx, ty, img2; };          // img2: image index over both problems
+    auto iter_begin = [&]() {
+        ItemIter it;
+        int v = it.item = blockIdx.x;
+        it.grp = v % a.groups; v /= a.groups; it.tx = v % a.tiles_x; v /= a.tiles_x; it.ty = v % a.tiles_y; it.img2 = v / a.tiles_y;
+        return it;
+    };
+    auto iter_next = [&](ItemIter& it) {
+        it.item += gridDim.x;
+        it.grp += a.d_grp; if (it.grp >= a.groups) { it.grp -= a.groups; ++it.tx; }
+        it.tx += a.d_tx;   if (it.tx >= a.tiles_x) { it.tx -= a.tiles_x; ++it.ty; }
+        it.ty += a.d_ty;   if (it.ty >= a.tiles_y) { it.ty -= a.tiles_y; ++it.img2; }
+        it.img2 += a.d_img;
+    };
+    auto decode = [&](const ItemIter& it) {
         Item w;
-        w.prob = item >= a.n_items_p ? 1 : 0; item -= w.prob * a.n_items_p;
-        const int grp = item % a.groups; int r = item / a.groups;
-        const int tx = r % a.tiles_x; r /= a.tiles_x;
-        const int ty = r % a.tiles_y; w.img = r / a.tiles_y;
-        w.oh0 = ty * TO; w.ow0 = tx * TO;
-        w.c_begin = grp * a.chunks_per_group; w.c_end = min(a.nchunks, w.c_begin + a.chunks_per_group);
+        w.prob = it.img2 >= a.B ? 1 : 0; w.img = it.img2 - w.prob * a.B;
+        w.oh0 = it.ty * TO; w.ow0 = it.tx * TO;
+        w.c_begin = it.grp * a.chunks_per_group; w.c_end = min(a.nchunks, w.c_begin + a.chunks_per_group);
         return w;
     };
 
@@ -165,8 +181,8 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
         if (lane == 0) {
             // ===== TMA producer: (x window, W1 chunk) per k-block, for every channel chunk =====
             int it = 0;
-            for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-                const Item w = decode(item);
+            for (ItemIter ii = iter_begin(); ii.item < a.n_items; iter_next(ii)) {
+                const Item w = decode(ii);
                 const int ey0 = w.oh0 * STRIDE - a.pad, ex0 = w.ow0 * STRIDE - a.pad;     // window origin in e / x coordinates
                 for (int c = w.c_begin; c < w.c_end; ++c)
                     for (int kb = 0; kb < a.nkb; ++kb, ++it) {
@@ -185,8 +201,8 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
         if (lane == 0) {
             // ===== MMA issuer =====
             int it = 0, cc = 0;                             // ring iteration / accumulator-buffer use counters
-            for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-              const Item w = decode(item);
+            for (ItemIter ii = iter_begin(); ii.item < a.n_items; iter_next(ii)) {
+              const Item w = decode(ii);
               for (int c = w.c_begin; c < w.c_end; ++c, ++cc) {
                 const int buf = cc & 1;
                 mbar_wait(&acc_empty[buf], ((uint32_t)(cc >> 1) & 1u) ^ 1u);
@@ -219,8 +235,8 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
     } else if (X3 && warp >= 2 + NUM_WORKERS / 32) {
         // ===== dedicated splitters: both halves of every landed x window, one ring stage at a time =====
         int it = 0;
-        for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-            const Item w = decode(item);
+        for (ItemIter ii = iter_begin(); ii.item < a.n_items; iter_next(ii)) {
+            const Item w = decode(ii);
             for (int c = w.c_begin; c < w.c_end; ++c)
                 for (int kb = 0; kb < a.nkb; ++kb, ++it) {
                     const int s = it % STAGES;
@@ -260,21 +276,31 @@ xdw_kernel(const __grid_constant__ XdwMaps mp, const XdwArgs a) {
         auto park_par = [&](int slot_idx, const float2& v) {
             if (par_owner) *reinterpret_cast<float2*>(PAR + slot_idx * (PAR_ROWS * NC) + prow * NC + pcol) = v;
         };
-        if ((int)blockIdx.x < a.n_items) { const Item w0 = decode(blockIdx.x); park_par(0, load_par(w0.prob, w0.c_begin)); }
+        ItemIter ii = iter_begin();
+        if (ii.item < a.n_items) { const Item w0 = decode(ii); park_par(0, load_par(w0.prob, w0.c_begin)); }
         worker_barrier();
+        // Depthwise role of this thread: output column dw_ox and row group dw_rg of the tile's valid columns x as many row groups
+        // as fit in the 32 slots.  A tile has TO columns / rows except in the last tile column / row: the thread's role for both
+        // column counts is worked out once here (bytes of `role`: ox full, rg full, ox edge, rg edge), the row grouping of the four
+        // tile kinds comes from the host (a.geom); the item loop only selects.
+        const int ncols_e = a.Wo - (a.tiles_x - 1) * TO, nrows_e = a.Ho - (a.tiles_y - 1) * TO;
+        const unsigned role = (unsigned)(slot % TO) | (unsigned)(slot / TO) << 8 | (unsigned)(slot % ncols_e) << 16 | (unsigned)(slot / ncols_e) << 24;
         int cc = 0;
-        for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-          const Item w = decode(item);
+        for (; ii.item < a.n_items;) {
+          const Item w = decode(ii);
           const int img = w.img, oh0 = w.oh0, ow0 = w.ow0;
           const int ey0 = oh0 * STRIDE - a.pad, ex0 = ow0 * STRIDE - a.pad;
-          // depthwise role of this thread for the tile: output column dw_ox, output rows [dw_oy0, dw_oy1)
-          // (the valid columns x as many row groups as fit in the 32 slots)
-          const int ncols = min(TO, a.Wo - ow0), nrows = min(TO, a.Ho - oh0);
-          const int n_rg = min(32 / ncols, nrows), rpt = (nrows + n_rg - 1) / n_rg;
-          const int dw_ox = slot % ncols, dw_rg = slot / ncols;
+          // this thread's output column dw_ox and output rows [dw_oy0, dw_oy1) of the tile
+          const bool col_e = ii.tx == a.tiles_x - 1, row_e = ii.ty == a.tiles_y - 1;
+          const int nrows = row_e ? nrows_e : TO;
+          const unsigned g8 = a.geom >> ((col_e ? 16 : 0) + (row_e ? 8 : 0));
+          const int rpt = (int)(g8 & 15u), n_rg = (int)((g8 >> 4) & 15u);
+          const unsigned r16 = role >> (col_e ? 16 : 0);
+          const int dw_ox = (int)(r16 & 255u), dw_rg = (int)((r16 >> 8) & 255u);
           const int dw_oy0 = dw_rg * rpt, dw_oy1 = dw_rg < n_rg ? min(nrows, dw_oy0 + rpt) : 0;
           int next_first = -1, next_prob = 0;              // first chunk (and problem) of this CTA's next item (-1: none)
-          if (item + (int)gridDim.x < a.n_items) { const Item wn = decode(item + gridDim.x); next_first = wn.c_begin; next_prob = wn.prob; }
+          iter_next(ii);
+          if (ii.item < a.n_items) { const Item wn = decode(ii); next_first = wn.c_begin; next_prob = wn.prob; }
           for (int c = w.c_begin; c < w.c_end; ++c, ++cc) {
             const int buf = cc & 1;
             const int ch0 = c * NC;
@@ -489,9 +515,15 @@ int xdw_conv(const XdwConv& p, cudaStream_t st, const XdwConv* p2) {
         if (g_prof_detail) tag = prof_shape_tag(tag, (long)px_out, p.Cin, p.mid);
         SMK_TAG(tag, 4.0 * (px_in * p.Cin + px_out * p.mid + (double)nprob * p.mid * (p.Cin + 13)), 2.0 * px_in * p.Cin * p.mid + 18.0 * px_out * p.mid, st);
     }
-    a.n_items_p = a.tiles_x * a.tiles_y * p.B * a.groups;
-    a.n_items = nprob * a.n_items_p;
+    a.B = p.B;
+    a.n_items = nprob * a.tiles_x * a.tiles_y * p.B * a.groups;
+    {
+        const int ncols_e = Wo - (a.tiles_x - 1) * TO, nrows_e = Ho - (a.tiles_y - 1) * TO;
+        auto group = [](int ncols, int nrows) { const int n_rg = std::min(32 / ncols, nrows); return (unsigned)((nrows + n_rg - 1) / n_rg) | (unsigned)n_rg << 4; };
+        a.geom = group(TO, TO) | group(TO, nrows_e) << 8 | group(ncols_e, TO) << 16 | group(ncols_e, nrows_e) << 24;
+    }
     dim3 grid((unsigned)std::min(a.n_items, p.w1t_lo ? std::min(slots, 148) : slots));            // persistent: (up to) 2 CTAs per SM
+    { int v = (int)grid.x; a.d_grp = v % a.groups; v /= a.groups; a.d_tx = v % a.tiles_x; v /= a.tiles_x; a.d_ty = v % a.tiles_y; a.d_img = v / a.tiles_y; }
     if (p.w1t_lo) {
         if (p.stride == 1) SMK_LAUNCH((xdw_kernel<1, 2>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3t, st, mp, a);
         else SMK_LAUNCH((xdw_kernel<2, 2>), dim3(grid), dim3(NUM_THREADS + NUM_SPLITTERS), smem3t, st, mp, a);

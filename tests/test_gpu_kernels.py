@@ -197,6 +197,8 @@ def tf_same_dw(e, wdw, stride):
     (3, 56, 24, 72, 2),         # stride 2: 56 -> 28 = 4x4 tiles of 7x7
     (2, 7, 160, 960, 1),        # 7x7: tile larger than the image, 15 chunks
     (1, 112, 16, 64, 2),        # the big one: 112 -> 56, 8x8 tiles, single chunk / k-block
+    (2, 20, 24, 72, 1),         # ragged tiles: 14 + 6 columns / rows (the edge role of the depthwise threads)
+    (3, 30, 16, 64, 2),         # stride 2, 30 -> 15 = 7 + 7 + 1: a one-pixel edge tile; the item stride carries through x, y and image
 ])
 def test_xdw_fused_kernel(native_lib, B, H, Cin, mid, stride):
     g = torch.Generator().manual_seed(31)
@@ -315,7 +317,8 @@ def test_gemm_tc3x_matches_fp64(native_lib, M, K, N, relu, use_res):
     assert err <= 4e-6 * ref.abs().max().item() * max(1.0, (K / 64) ** 0.5), "max err %.3g vs scale %.3g" % (err, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("B,H,Cin,mid,stride", [(2, 28, 40, 120, 1), (1, 14, 80, 200, 1), (3, 56, 24, 72, 2), (1, 112, 16, 64, 2), (2, 14, 112, 672, 1)])
+@pytest.mark.parametrize("B,H,Cin,mid,stride", [(2, 28, 40, 120, 1), (1, 14, 80, 200, 1), (3, 56, 24, 72, 2), (1, 112, 16, 64, 2), (2, 14, 112, 672, 1),
+                                                   (2, 20, 24, 72, 1), (3, 30, 16, 64, 2), (40, 28, 40, 120, 1)])
 def test_xdw3x_matches_fp64(native_lib, B, H, Cin, mid, stride):
     g = torch.Generator().manual_seed(62)
     x = torch.randn(B, Cin, H, H, generator=g)
