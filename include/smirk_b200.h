@@ -216,6 +216,19 @@ int smk_masking_forward(const SmkMasking* h, const float* img, const float* hull
                         int64_t* dbg_rbound, float* dbg_noise, float* dbg_centres, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Peer-mapped gather buffers: the all-gather of the final outputs across the GPUs of one node (the
+ * reference has no multi-GPU code) as copy-engine pushes over NVLink, which take no SM from the persistent compute
+ * kernels.  Each rank: smk_peer_alloc a [world][shard] buffer, exchange the 64-byte handles (any host channel),
+ * smk_peer_open every peer's handle, and after a batch smk_peer_push its packed shard into slot `rank` of every buffer
+ * on a communication stream.  Allocation and mapping are set-up calls; a forward never allocates.
+ * ---------------------------------------------------------------------------------------------- */
+int smk_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int smk_peer_free(void* ptr);
+int smk_peer_open(const unsigned char* handle64, void** ptr);
+int smk_peer_close(void* ptr);
+int smk_peer_push(void* dst, const void* src, size_t bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Kernel-level test entry points (used by tests/ to check single convolution kernels against torch;
  * not part of the drop-in surface).  All pointers are device pointers.
  *   smk_debug_conv_f32: fp32 CUDA-core implicit GEMM.  w_kn is [K][N]; mode 0 = 1x1, 1 = 3x3 zero pad,

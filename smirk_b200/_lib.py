@@ -54,7 +54,8 @@ SYMBOLS = ["smk_version", "smk_last_error", "smk_launch_count", "smk_profiler_en
            "smk_debug_conv_f32", "smk_debug_conv_tc", "smk_debug_reflect_halo", "smk_debug_xdw", "smk_debug_stem_ds", "smk_debug_gemm_tc3x", "smk_debug_xdw3x", "smk_debug_conv3_win",
            "smk_warp_workspace_bytes", "smk_crop_warp", "smk_warp_u8", "smk_f32chw_to_u8hwc",
            "smk_masking_create", "smk_masking_destroy", "smk_masking_workspace_bytes", "smk_masking_face_weights",
-           "smk_masking_points", "smk_masking_compose", "smk_masking_forward_workspace_bytes", "smk_masking_forward", "smk_masking_transfer_pixels"]
+           "smk_masking_points", "smk_masking_compose", "smk_masking_forward_workspace_bytes", "smk_masking_forward", "smk_masking_transfer_pixels",
+           "smk_peer_alloc", "smk_peer_free", "smk_peer_open", "smk_peer_close", "smk_peer_push"]
 
 
 def lib():
@@ -109,6 +110,11 @@ def lib():
     L.smk_masking_forward.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, C.c_float, C.c_float, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.smk_masking_compose.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, i, i, vp, vp, sz, vp]
     L.smk_masking_transfer_pixels.argtypes = [vp, vp, vp, vp, i, i, i, vp, vp, sz, vp]
+    L.smk_peer_alloc.argtypes = [sz, C.POINTER(vp), C.c_char_p]
+    L.smk_peer_free.argtypes = [vp]
+    L.smk_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.smk_peer_close.argtypes = [vp]
+    L.smk_peer_push.argtypes = [vp, vp, sz, vp]
     L.smk_debug_conv3_win.argtypes = [vp, i, i, i, i, i, vp, vp, vp, i, i, vp, i, vp]
     L.smk_debug_gemm_tc3x.argtypes = [vp, i, i, vp, vp, vp, vp, i, i, i, vp, i, vp, i, vp]
     L.smk_debug_xdw3x.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp]

@@ -76,6 +76,47 @@ class _Lane:
         return [m for m in (self.encoder, self.flame, self.renderer, self.generator, self.masking) if m is not None]
 
 
+class _PeerBuffer:
+    """One rank's gather buffer of one lane, allocated by the native library (``smk_peer_alloc``: a plain cudaMalloc whose
+    CUDA IPC handle other ranks can open) plus this rank's mappings of every peer's buffer.  ``local`` is a uint8 tensor view
+    of the own buffer, ``ptrs[r]`` the device address of rank r's buffer as seen from this process."""
+
+    def __init__(self, nbytes, device):
+        import ctypes as C
+        L = _lib.lib()
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        _lib.check(L.smk_peer_alloc(nbytes, C.byref(ptr), handle), "smk_peer_alloc")
+        self.ptr, self.nbytes, self.handle, self.ptrs, self._mapped = ptr.value, nbytes, handle.raw, [], []
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+        self.local = torch.as_tensor(self, device=device)
+
+    def map_peers(self, handles, rank):
+        import ctypes as C
+        L = _lib.lib()
+        for r, h in enumerate(handles):
+            if r == rank:
+                self.ptrs.append(self.ptr)
+                continue
+            p = C.c_void_p()
+            _lib.check(L.smk_peer_open(h, C.byref(p)), "smk_peer_open")
+            self._mapped.append(p.value)
+            self.ptrs.append(p.value)
+        self.local = self.local.view(len(handles), -1)
+
+    def __del__(self):
+        try:
+            L = _lib.lib()
+            for p in self._mapped:
+                L.smk_peer_close(p)
+            self._mapped = []
+            if self.ptr:
+                self.local = None
+                L.smk_peer_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
 class SmirkPipeline:
     OUT_KEYS = ("rendered_img", "vertices", "transformed_vertices", "landmarks_fan", "landmarks_mp", "params")
 
@@ -202,15 +243,14 @@ class SmirkPipeline:
         """After every batch, all-gather the listed outputs over the process group (dim 0 = rank-major frames) on a
         communication stream; results land in ``gathered(i, key)``.  ``keys = ()`` switches it off.
 
-        backend "nccl" (= "auto"): ``all_gather_into_tensor`` over NVLink 5 / NVSwitch; NCCL's kernels take SMs from the
-        compute kernels they overlap with: measured -4.7 % (B = 32) / -3.6 % (full cycle, B = 256) at 2 GPUs.
-        backend "p2p" (experimental): every rank's gather buffers are mapped into all ranks of the node (CUDA IPC) and
-        each rank PUSHES its shard into its slice of every peer's buffer with device-to-device copies on the communication
-        stream.  Results identical to NCCL (tools/check_gather.py), but torch's cross-device ``copy_`` serialises on the
-        peer device's stream and reached only 17 GB/s per rank at 21 MB per step: 26.1k instead of 65.6k faces/s at B = 32,
-        -5.7 % at B = 256 (profiles/r02_bench_n2_p2p_gather.json) — kept for the comparison, not the default.  A slot of a
-        peer's buffer is rewritten ``slots`` batches later; ``gather_sync()`` (stream join + group barrier) makes a batch's
-        gathered tensors safe to read."""
+        backend "p2p" (= "auto" when every rank can map its peers): each rank owns one gather buffer per lane, maps every
+        peer's buffer once (CUDA IPC, ``smk_peer_*`` in the C ABI) and after a batch PUSHES its packed shard into slot
+        ``rank`` of every buffer with copy-engine copies on the communication stream (csrc/peer.cu) — no SM is taken from the
+        persistent compute kernels.  A slot of a peer's buffer is rewritten ``slots`` batches later; ``gather_sync()``
+        (stream join + group barrier) makes a batch's gathered tensors safe to read.
+        backend "nccl": ``all_gather_into_tensor`` over NVLink 5 / NVSwitch.  NCCL's kernels occupy SMs while the compute
+        kernels (148 persistent CTAs each) run, which splits every overlapped launch into two waves: measured 0.85 (B = 32) /
+        0.89 (full cycle, B = 256) of the no-gather throughput at 8 GPUs (profiles/r02_bench_n8_nccl_gather.json)."""
         import torch.distributed as dist
         self._gather_keys = tuple(keys) if (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1) else ()
         self._gather_group = group
@@ -218,26 +258,22 @@ class SmirkPipeline:
         if self._gather_keys:
             if self._comm is None:
                 self._comm = torch.cuda.Stream(device=self.device)
-            self._gather_backend = "pending-p2p" if backend == "p2p" else "nccl"
+            self._gather_backend = "nccl" if backend == "nccl" else "pending-" + backend
         return self._gather_keys
 
     def _setup_p2p(self, B):
         """Allocate one packed gather buffer per lane ([world, bytes of one shard]) and map every peer's buffers (CUDA IPC).
         Collective: every rank must call it with the same B.  Returns True when every rank succeeded."""
         import torch.distributed as dist
-        from torch.multiprocessing.reductions import reduce_tensor
         ws, rank = dist.get_world_size(self._gather_group), dist.get_rank(self._gather_group)
-        ok, sizes, shard = True, [], 0
+        ok, sizes, shard, mine, bufs = True, [], 0, None, []
         try:
             rec = self.capture(B)
             sizes = [rec["out"][k].numel() * rec["out"][k].element_size() for k in self._gather_keys]
             shard = sum((n + 255) // 256 * 256 for n in sizes)
-            mine = []
-            for lane in range(self.slots):
-                L = self._lane(lane)
-                L.p2p_buf = torch.empty(ws, shard, dtype=torch.uint8, device=self.device)
-                L.p2p_stage = torch.empty(shard, dtype=torch.uint8, device=self.device)
-                mine.append(reduce_tensor(L.p2p_buf))
+            with torch.cuda.device(self.device):
+                bufs = [_PeerBuffer(ws * shard, self.device) for _ in range(self.slots)]
+            mine = [b.handle for b in bufs]
         except Exception:
             ok, mine = False, None
         everyone = [None] * ws
@@ -245,16 +281,12 @@ class SmirkPipeline:
         ok = ok and all(e is not None for e in everyone)
         if ok:
             try:
-                for lane in range(self.slots):
-                    L = self._lanes[lane]
-                    L.p2p_peers = []
-                    for r in range(ws):
-                        if r == rank:
-                            L.p2p_peers.append(L.p2p_buf)
-                        else:
-                            fn, fargs = everyone[r][lane]
-                            L.p2p_peers.append(fn(*fargs))             # the peer's buffer, mapped into this process
-                    L.p2p_peers[(rank + 1) % ws][rank, :16].copy_(L.p2p_stage[:16])      # touch one peer: enables peer access now
+                with torch.cuda.device(self.device):
+                    for lane in range(self.slots):
+                        L = self._lane(lane)
+                        L.p2p = bufs[lane]
+                        L.p2p.map_peers([everyone[r][lane] for r in range(ws)], rank)
+                        L.p2p_stage = torch.empty(shard, dtype=torch.uint8, device=self.device)
                 torch.cuda.synchronize(self.device)
             except Exception:
                 ok = False
@@ -283,9 +315,10 @@ class SmirkPipeline:
                 for k, n in zip(self._gather_keys, self._p2p["sizes"]):          # pack the shard (device-local copies)
                     L.p2p_stage[off:off + n].copy_(rec["out"][k].reshape(-1).view(torch.uint8), non_blocking=True)
                     off += (n + 255) // 256 * 256
-                for d in range(ws):                                             # push it to every rank's slice `rank`, peers first
+                shard, src = self._p2p["shard"], L.p2p_stage.data_ptr()
+                for d in range(ws):                                             # push it to slot `rank` of every rank's buffer, peers first
                     r = (rank + 1 + d) % ws
-                    L.p2p_peers[r][rank].copy_(L.p2p_stage, non_blocking=True)
+                    _lib.check(_lib.lib().smk_peer_push(L.p2p.ptrs[r] + rank * shard, src, shard, self._comm.cuda_stream), "smk_peer_push")
                 L.gathered.record(self._comm)
             return
         with torch.cuda.stream(self._comm):
@@ -316,7 +349,7 @@ class SmirkPipeline:
             for k, n in zip(self._gather_keys, self._p2p["sizes"]):
                 if k == key:
                     t = rec["out"][k]
-                    return L.p2p_buf[:, off:off + n].contiguous().view(t.dtype).reshape((-1,) + tuple(t.shape[1:]))
+                    return L.p2p.local[:, off:off + n].contiguous().view(t.dtype).reshape((-1,) + tuple(t.shape[1:]))
                 off += (n + 255) // 256 * 256
             raise KeyError(key)
         for (k, _), v in L.gather_out.items():
