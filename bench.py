@@ -339,7 +339,7 @@ def run_workload(cx, args, B, generator, slots, R, with_cpu):
                   "host_checksum": float(cx.last["params"].double().abs().sum())}          # touches the host result
     if gather_keys:
         gb = pipe.gather_bytes_per_step(B)
-        how = {"nccl": "NCCL all_gather_into_tensor", "p2p": "peer-to-peer pushes (CUDA IPC-mapped gather buffers, copy engines over NVLink)"}.get(pipe._gather_backend, str(pipe._gather_backend))
+        how = {"nccl": "NCCL all_gather_into_tensor", "p2p": "copy-engine pushes of every output into the CUDA-IPC mapped gather buffers of the peers over NVLink (csrc/peer.cu; own shard stays in place)"}.get(pipe._gather_backend, str(pipe._gather_backend))
         out["gather"] = {"backend": pipe._gather_backend,
                          "collective": "%s of %s per step, on a communication stream inside the timed region" % (how, "+".join(gather_keys)),
                          "recv_bytes_per_rank_per_step": gb, "recv_gbs_per_rank": gb / (out["ms_per_step"] * 1e-3) / 1e9}

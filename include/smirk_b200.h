@@ -227,6 +227,12 @@ int smk_peer_free(void* ptr);
 int smk_peer_open(const unsigned char* handle64, void** ptr);
 int smk_peer_close(void* ptr);
 int smk_peer_push(void* dst, const void* src, size_t bytes, void* stream);
+/* The same copy to n destinations, spread over the fan's own streams (several copy engines / NVLink ports at once);
+ * ordered after the work already on `stream`, which resumes only after every copy.                                        */
+typedef struct SmkPeerFan SmkPeerFan;
+int smk_peer_fan_create(int n_streams, SmkPeerFan** out);
+void smk_peer_fan_destroy(SmkPeerFan* f);
+int smk_peer_fan_push(SmkPeerFan* f, void* const* dsts, int n, const void* src, size_t bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Kernel-level test entry points (used by tests/ to check single convolution kernels against torch;

@@ -55,7 +55,8 @@ SYMBOLS = ["smk_version", "smk_last_error", "smk_launch_count", "smk_profiler_en
            "smk_warp_workspace_bytes", "smk_crop_warp", "smk_warp_u8", "smk_f32chw_to_u8hwc",
            "smk_masking_create", "smk_masking_destroy", "smk_masking_workspace_bytes", "smk_masking_face_weights",
            "smk_masking_points", "smk_masking_compose", "smk_masking_forward_workspace_bytes", "smk_masking_forward", "smk_masking_transfer_pixels",
-           "smk_peer_alloc", "smk_peer_free", "smk_peer_open", "smk_peer_close", "smk_peer_push"]
+           "smk_peer_alloc", "smk_peer_free", "smk_peer_open", "smk_peer_close", "smk_peer_push",
+           "smk_peer_fan_create", "smk_peer_fan_destroy", "smk_peer_fan_push"]
 
 
 def lib():
@@ -115,6 +116,10 @@ def lib():
     L.smk_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.smk_peer_close.argtypes = [vp]
     L.smk_peer_push.argtypes = [vp, vp, sz, vp]
+    L.smk_peer_fan_create.argtypes = [i, C.POINTER(vp)]
+    L.smk_peer_fan_destroy.argtypes = [vp]
+    L.smk_peer_fan_destroy.restype = None
+    L.smk_peer_fan_push.argtypes = [vp, C.POINTER(vp), i, vp, sz, vp]
     L.smk_debug_conv3_win.argtypes = [vp, i, i, i, i, i, vp, vp, vp, i, i, vp, i, vp]
     L.smk_debug_gemm_tc3x.argtypes = [vp, i, i, vp, vp, vp, vp, i, i, i, vp, i, vp, i, vp]
     L.smk_debug_xdw3x.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp]

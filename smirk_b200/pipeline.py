@@ -90,7 +90,9 @@ class _PeerBuffer:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
         self.local = torch.as_tensor(self, device=device)
 
-    def map_peers(self, handles, rank):
+    def map_peers(self, handles, rank, shard, offsets=(0,)):
+        """Open every peer's handle; ``dsts[j]`` = where part j (byte offset ``offsets[j]``) of this rank's shard goes in each
+        PEER's buffer (slot ``rank``), starting with the next rank.  The own slot is not a destination: see ``SmirkPipeline.gathered``."""
         import ctypes as C
         L = _lib.lib()
         for r, h in enumerate(handles):
@@ -102,6 +104,8 @@ class _PeerBuffer:
             self._mapped.append(p.value)
             self.ptrs.append(p.value)
         self.local = self.local.view(len(handles), -1)
+        ws = len(handles)
+        self.dsts = [(C.c_void_p * (ws - 1))(*[self.ptrs[(rank + 1 + d) % ws] + rank * shard + off for d in range(ws - 1)]) for off in offsets]
 
     def __del__(self):
         try:
@@ -244,10 +248,11 @@ class SmirkPipeline:
         communication stream; results land in ``gathered(i, key)``.  ``keys = ()`` switches it off.
 
         backend "p2p" (= "auto" when every rank can map its peers): each rank owns one gather buffer per lane, maps every
-        peer's buffer once (CUDA IPC, ``smk_peer_*`` in the C ABI) and after a batch PUSHES its packed shard into slot
-        ``rank`` of every buffer with copy-engine copies on the communication stream (csrc/peer.cu) — no SM is taken from the
-        persistent compute kernels.  A slot of a peer's buffer is rewritten ``slots`` batches later; ``gather_sync()``
-        (stream join + group barrier) makes a batch's gathered tensors safe to read.
+        peer's buffer once (CUDA IPC, ``smk_peer_*`` in the C ABI) and after a batch PUSHES every output into slot ``rank``
+        of every peer's buffer with copy-engine copies (csrc/peer.cu) — no SM is taken from the persistent compute kernels and
+        nothing is copied inside the GPU (the own shard stays in the output tensor until ``gathered()`` is called).  A slot of
+        a peer's buffer is rewritten ``slots`` batches later; ``gather_sync()`` (stream join + group barrier) makes a batch's
+        gathered tensors safe to read.
         backend "nccl": ``all_gather_into_tensor`` over NVLink 5 / NVSwitch.  NCCL's kernels occupy SMs while the compute
         kernels (148 persistent CTAs each) run, which splits every overlapped launch into two waves: measured 0.85 (B = 32) /
         0.89 (full cycle, B = 256) of the no-gather throughput at 8 GPUs (profiles/r02_bench_n8_nccl_gather.json)."""
@@ -266,10 +271,12 @@ class SmirkPipeline:
         Collective: every rank must call it with the same B.  Returns True when every rank succeeded."""
         import torch.distributed as dist
         ws, rank = dist.get_world_size(self._gather_group), dist.get_rank(self._gather_group)
-        ok, sizes, shard, mine, bufs = True, [], 0, None, []
+        ok, sizes, offsets, shard, mine, bufs = True, [], [], 0, None, []
         try:
             rec = self.capture(B)
+            assert all(rec["out"][k].is_contiguous() for k in self._gather_keys)
             sizes = [rec["out"][k].numel() * rec["out"][k].element_size() for k in self._gather_keys]
+            offsets = [sum((m + 255) // 256 * 256 for m in sizes[:j]) for j in range(len(sizes))]
             shard = sum((n + 255) // 256 * 256 for n in sizes)
             with torch.cuda.device(self.device):
                 bufs = [_PeerBuffer(ws * shard, self.device) for _ in range(self.slots)]
@@ -285,15 +292,18 @@ class SmirkPipeline:
                     for lane in range(self.slots):
                         L = self._lane(lane)
                         L.p2p = bufs[lane]
-                        L.p2p.map_peers([everyone[r][lane] for r in range(ws)], rank)
-                        L.p2p_stage = torch.empty(shard, dtype=torch.uint8, device=self.device)
+                        L.p2p.map_peers([everyone[r][lane] for r in range(ws)], rank, shard, offsets)
+                    import ctypes as C
+                    fan = C.c_void_p()
+                    _lib.check(_lib.lib().smk_peer_fan_create(min(ws, 8), C.byref(fan)), "smk_peer_fan_create")
+                    self._fan = _lib.NativeHandle(fan, "smk_peer_fan_destroy")
                 torch.cuda.synchronize(self.device)
             except Exception:
                 ok = False
         flag = torch.tensor([1 if ok else 0], device=self.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self._gather_group)
         ok = bool(flag.item())
-        self._p2p = dict(B=B, sizes=sizes, shard=shard) if ok else None
+        self._p2p = dict(B=B, sizes=sizes, offsets=offsets, shard=shard, rank=rank) if ok else None
         return ok
 
     def _gather(self, L, rec):
@@ -308,17 +318,15 @@ class SmirkPipeline:
         if self._gather_backend == "p2p" and self._p2p["B"] != B:
             self._gather_backend = "p2p" if self._setup_p2p(B) else "nccl"
         if self._gather_backend == "p2p":
-            rank = dist.get_rank(self._gather_group)
+            # Every output goes from where the kernels wrote it straight into slot `rank` of each peer's buffer: one copy-engine
+            # copy per (output, peer) on the fan's streams.  No packing and no copy of the own shard — device-local copies are
+            # what hurts the concurrent compute kernels (tools/bench_peer_load.py: 7 x 21 MB inside the GPU cost the B = 32
+            # pipeline 42 %, the same bytes pushed to a peer 3.8 %).
             with torch.cuda.stream(self._comm):
                 self._comm.wait_event(L.computed)
-                off = 0
-                for k, n in zip(self._gather_keys, self._p2p["sizes"]):          # pack the shard (device-local copies)
-                    L.p2p_stage[off:off + n].copy_(rec["out"][k].reshape(-1).view(torch.uint8), non_blocking=True)
-                    off += (n + 255) // 256 * 256
-                shard, src = self._p2p["shard"], L.p2p_stage.data_ptr()
-                for d in range(ws):                                             # push it to slot `rank` of every rank's buffer, peers first
-                    r = (rank + 1 + d) % ws
-                    _lib.check(_lib.lib().smk_peer_push(L.p2p.ptrs[r] + rank * shard, src, shard, self._comm.cuda_stream), "smk_peer_push")
+                for j, (k, n) in enumerate(zip(self._gather_keys, self._p2p["sizes"])):
+                    _lib.check(_lib.lib().smk_peer_fan_push(self._fan, L.p2p.dsts[j], ws - 1, rec["out"][k].data_ptr(), n,
+                                                            self._comm.cuda_stream), "smk_peer_fan_push")
                 L.gathered.record(self._comm)
             return
         with torch.cuda.stream(self._comm):
@@ -345,25 +353,23 @@ class SmirkPipeline:
         L = self._lanes[i % self.slots]
         if self._gather_backend == "p2p":
             rec = L.graphs[self._p2p["B"]]
-            off = 0
-            for k, n in zip(self._gather_keys, self._p2p["sizes"]):
-                if k == key:
-                    t = rec["out"][k]
-                    return L.p2p.local[:, off:off + n].contiguous().view(t.dtype).reshape((-1,) + tuple(t.shape[1:]))
-                off += (n + 255) // 256 * 256
-            raise KeyError(key)
+            j = self._gather_keys.index(key)
+            off, n, t = self._p2p["offsets"][j], self._p2p["sizes"][j], rec["out"][key]
+            # the own shard was never copied: it still sits in the pipeline's output tensor and joins the peers' shards here
+            L.p2p.local[self._p2p["rank"], off:off + n].copy_(t.reshape(-1).view(torch.uint8))
+            return L.p2p.local[:, off:off + n].contiguous().view(t.dtype).reshape((-1,) + tuple(t.shape[1:]))
         for (k, _), v in L.gather_out.items():
             if k == key:
                 return v
         raise KeyError(key)
 
     def gather_bytes_per_step(self, B):
-        """Bytes this rank RECEIVES per step in the all-gather (world_size x its own shard)."""
+        """Bytes this rank RECEIVES per step in the all-gather ((world_size - 1) shards; it sends as many)."""
         if not self._gather_keys:
             return 0
         import torch.distributed as dist
         rec = self.capture(B)
-        return dist.get_world_size(self._gather_group) * sum(rec["out"][k].numel() * rec["out"][k].element_size() for k in self._gather_keys)
+        return (dist.get_world_size(self._gather_group) - 1) * sum(rec["out"][k].numel() * rec["out"][k].element_size() for k in self._gather_keys)
 
     def join(self):
         cur = torch.cuda.current_stream(self.device)
