@@ -23,6 +23,7 @@ Captured graphs snapshot the packed weights and workspaces they were recorded wi
 (``rec["keep"]``); after changing weights, ``precision`` or devices call ``refresh()`` to re-capture.
 """
 import copy
+import os
 
 import torch
 
@@ -249,8 +250,9 @@ class SmirkPipeline:
 
         backend "p2p" (= "auto" when every rank can map its peers): each rank owns one gather buffer per lane, maps every
         peer's buffer once (CUDA IPC, ``smk_peer_*`` in the C ABI) and after a batch PUSHES every output into slot ``rank``
-        of every peer's buffer with copy-engine copies (csrc/peer.cu) — no SM is taken from the persistent compute kernels and
-        nothing is copied inside the GPU (the own shard stays in the output tensor until ``gathered()`` is called).  A slot of
+        of every peer's buffer with copy-engine copies (csrc/peer.cu; directly from the output tensors with one peer, packed
+        first with more: see ``_gather``) — no SM is taken from the persistent compute kernels, and the own shard stays in the
+        output tensor until ``gathered()`` is called.  A slot of
         a peer's buffer is rewritten ``slots`` batches later; ``gather_sync()`` (stream join + group barrier) makes a batch's
         gathered tensors safe to read.
         backend "nccl": ``all_gather_into_tensor`` over NVLink 5 / NVSwitch.  NCCL's kernels occupy SMs while the compute
@@ -272,6 +274,7 @@ class SmirkPipeline:
         import torch.distributed as dist
         ws, rank = dist.get_world_size(self._gather_group), dist.get_rank(self._gather_group)
         ok, sizes, offsets, shard, mine, bufs = True, [], [], 0, None, []
+        pack = int(os.environ.get("SMK_GATHER_PACK", "1" if ws > 2 else "0")) != 0
         try:
             rec = self.capture(B)
             assert all(rec["out"][k].is_contiguous() for k in self._gather_keys)
@@ -293,6 +296,7 @@ class SmirkPipeline:
                         L = self._lane(lane)
                         L.p2p = bufs[lane]
                         L.p2p.map_peers([everyone[r][lane] for r in range(ws)], rank, shard, offsets)
+                        L.p2p_stage = torch.empty(shard, dtype=torch.uint8, device=self.device) if pack else None
                     import ctypes as C
                     fan = C.c_void_p()
                     _lib.check(_lib.lib().smk_peer_fan_create(min(ws, 8), C.byref(fan)), "smk_peer_fan_create")
@@ -303,7 +307,7 @@ class SmirkPipeline:
         flag = torch.tensor([1 if ok else 0], device=self.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self._gather_group)
         ok = bool(flag.item())
-        self._p2p = dict(B=B, sizes=sizes, offsets=offsets, shard=shard, rank=rank) if ok else None
+        self._p2p = dict(B=B, sizes=sizes, offsets=offsets, shard=shard, rank=rank, pack=pack) if ok else None
         return ok
 
     def _gather(self, L, rec):
@@ -318,15 +322,25 @@ class SmirkPipeline:
         if self._gather_backend == "p2p" and self._p2p["B"] != B:
             self._gather_backend = "p2p" if self._setup_p2p(B) else "nccl"
         if self._gather_backend == "p2p":
-            # Every output goes from where the kernels wrote it straight into slot `rank` of each peer's buffer: one copy-engine
-            # copy per (output, peer) on the fan's streams.  No packing and no copy of the own shard — device-local copies are
-            # what hurts the concurrent compute kernels (tools/bench_peer_load.py: 7 x 21 MB inside the GPU cost the B = 32
-            # pipeline 42 %, the same bytes pushed to a peer 3.8 %).
+            # Copy-engine copies into slot `rank` of each PEER's buffer on the fan's streams; the own shard is never copied.
+            #   direct (one peer): every output goes from where the kernels wrote it, one copy per (output, peer) — device-local
+            #     copies are what hurts the concurrent compute kernels (tools/bench_peer_load.py: 7 x 21 MB inside the GPU cost
+            #     the B = 32 pipeline 42 %, the same bytes pushed to a peer 3.8 %): 0.999 of the no-gather throughput at 2 GPUs
+            #     against 0.972 with a pack copy first.
+            #   packed (more peers): the outputs are first packed into one staging buffer and each peer gets ONE copy.  At
+            #     8 GPUs the 21 copies per batch of the direct form measured 226k faces/s end to end against 260k packed
+            #     (device-resident: 250k vs 249k); profiles/r02_bench_n8_*.json.
             with torch.cuda.stream(self._comm):
                 self._comm.wait_event(L.computed)
-                for j, (k, n) in enumerate(zip(self._gather_keys, self._p2p["sizes"])):
-                    _lib.check(_lib.lib().smk_peer_fan_push(self._fan, L.p2p.dsts[j], ws - 1, rec["out"][k].data_ptr(), n,
+                if self._p2p["pack"]:
+                    for k, n, off in zip(self._gather_keys, self._p2p["sizes"], self._p2p["offsets"]):
+                        L.p2p_stage[off:off + n].copy_(rec["out"][k].reshape(-1).view(torch.uint8), non_blocking=True)
+                    _lib.check(_lib.lib().smk_peer_fan_push(self._fan, L.p2p.dsts[0], ws - 1, L.p2p_stage.data_ptr(), self._p2p["shard"],
                                                             self._comm.cuda_stream), "smk_peer_fan_push")
+                else:
+                    for j, (k, n) in enumerate(zip(self._gather_keys, self._p2p["sizes"])):
+                        _lib.check(_lib.lib().smk_peer_fan_push(self._fan, L.p2p.dsts[j], ws - 1, rec["out"][k].data_ptr(), n,
+                                                                self._comm.cuda_stream), "smk_peer_fan_push")
                 L.gathered.record(self._comm)
             return
         with torch.cuda.stream(self._comm):
