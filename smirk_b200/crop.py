@@ -93,7 +93,9 @@ def _matrices(tforms, invert, device):
         if not (p[2, 0] == 0.0 and p[2, 1] == 0.0 and p[2, 2] == 1.0):
             raise ValueError("only affine transforms (last row 0 0 1) are supported")
         mats.append(np.linalg.inv(p) if invert else p)
-    return torch.from_numpy(np.ascontiguousarray(np.stack(mats))).to(device)
+    # pinned staging + asynchronous upload on the caller's stream: a pageable copy would stall the pipeline on every call
+    host = torch.from_numpy(np.ascontiguousarray(np.stack(mats))).pin_memory()
+    return host.to(device, non_blocking=True), host
 
 
 def _workspace(L, B, device):
@@ -115,10 +117,11 @@ def crop_to_tensor(frames, tforms, image_size=224, bgr=True):
     out = torch.empty(B, 3, image_size, image_size, dtype=torch.float32, device=frames.device)
     if B == 0:
         return out
-    m = _matrices(tforms, True, frames.device)
-    ws, n = _workspace(L, B, frames.device)
-    _lib.check(L.smk_crop_warp(frames.data_ptr(), B, H, W, m.data_ptr(), image_size, 1 if bgr else 0, out.data_ptr(),
-                               ws.data_ptr(), n, _lib.stream_ptr(frames.device)), "smk_crop_warp")
+    with torch.cuda.device(frames.device):                 # launches go to the frames' device, not the current one
+        m, _pinned = _matrices(tforms, True, frames.device)
+        ws, n = _workspace(L, B, frames.device)
+        _lib.check(L.smk_crop_warp(frames.data_ptr(), B, H, W, m.data_ptr(), image_size, 1 if bgr else 0, out.data_ptr(),
+                                   ws.data_ptr(), n, _lib.stream_ptr(frames.device)), "smk_crop_warp")
     return out
 
 
@@ -137,10 +140,11 @@ def warp_back(rendered, tforms, out_hw):
     out = torch.empty(B, H, W, 3, dtype=torch.uint8, device=rendered.device)
     if B == 0:
         return out
-    st = _lib.stream_ptr(rendered.device)
-    u8 = torch.empty(B, S, S, 3, dtype=torch.uint8, device=rendered.device)
-    _lib.check(L.smk_f32chw_to_u8hwc(rendered.data_ptr(), B, S, u8.data_ptr(), st), "smk_f32chw_to_u8hwc")
-    m = _matrices(tforms, False, rendered.device)
-    ws, n = _workspace(L, B, rendered.device)
-    _lib.check(L.smk_warp_u8(u8.data_ptr(), B, S, S, m.data_ptr(), H, W, out.data_ptr(), ws.data_ptr(), n, st), "smk_warp_u8")
+    with torch.cuda.device(rendered.device):
+        st = _lib.stream_ptr(rendered.device)
+        u8 = torch.empty(B, S, S, 3, dtype=torch.uint8, device=rendered.device)
+        _lib.check(L.smk_f32chw_to_u8hwc(rendered.data_ptr(), B, S, u8.data_ptr(), st), "smk_f32chw_to_u8hwc")
+        m, _pinned = _matrices(tforms, False, rendered.device)
+        ws, n = _workspace(L, B, rendered.device)
+        _lib.check(L.smk_warp_u8(u8.data_ptr(), B, S, S, m.data_ptr(), H, W, out.data_ptr(), ws.data_ptr(), n, st), "smk_warp_u8")
     return out
