@@ -335,13 +335,18 @@ class SmirkPipeline:
                 if self._p2p["pack"]:
                     for k, n, off in zip(self._gather_keys, self._p2p["sizes"], self._p2p["offsets"]):
                         L.p2p_stage[off:off + n].copy_(rec["out"][k].reshape(-1).view(torch.uint8), non_blocking=True)
+                    # The lane may overwrite its outputs as soon as they are PACKED: the pushes read the staging buffer only, and
+                    # its reuse is ordered by this stream (a fan push ends with the stream waiting for every copy).  Releasing
+                    # the lane after the pushes instead idles it for their whole duration — with 7 peers 0.3 of the 3.6 ms a
+                    # B = 32 batch spends on its lane, which is the 11 % the 8-GPU runs lost.
+                    L.gathered.record(self._comm)
                     _lib.check(_lib.lib().smk_peer_fan_push(self._fan, L.p2p.dsts[0], ws - 1, L.p2p_stage.data_ptr(), self._p2p["shard"],
                                                             self._comm.cuda_stream), "smk_peer_fan_push")
                 else:
                     for j, (k, n) in enumerate(zip(self._gather_keys, self._p2p["sizes"])):
                         _lib.check(_lib.lib().smk_peer_fan_push(self._fan, L.p2p.dsts[j], ws - 1, rec["out"][k].data_ptr(), n,
                                                                 self._comm.cuda_stream), "smk_peer_fan_push")
-                L.gathered.record(self._comm)
+                    L.gathered.record(self._comm)
             return
         with torch.cuda.stream(self._comm):
             self._comm.wait_event(L.computed)
