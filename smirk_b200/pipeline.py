@@ -109,15 +109,15 @@ class _PeerBuffer:
         self.dsts = [(C.c_void_p * (ws - 1))(*[self.ptrs[(rank + 1 + d) % ws] + rank * shard + off for d in range(ws - 1)]) for off in offsets]
 
     def __del__(self):
+        # Only this process's mappings of the PEERS' buffers are closed here.  The own buffer is exported: CUDA leaves freeing
+        # it while another process may still have it mapped undefined, and a destructor cannot synchronise with the peers, so
+        # it is left to process teardown (a gather set-up is made once per pipeline; bench.py's two pipelines hold 0.7 + 5.9 GB
+        # at 8 GPUs).  A host that re-creates pipelines can call smk_peer_free itself after a barrier.
         try:
             L = _lib.lib()
             for p in self._mapped:
                 L.smk_peer_close(p)
             self._mapped = []
-            if self.ptr:
-                self.local = None
-                L.smk_peer_free(self.ptr)
-                self.ptr = None
         except Exception:
             pass
 
