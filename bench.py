@@ -509,11 +509,14 @@ def main():
         line = {
             "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"tf32x3": "tf32x3 (tcgen05 TF32 products, 3-term error-compensated = fp32-equivalent; fp32 accumulate), f32 elsewhere",
-                      "tf32": "tf32 convs (fp32 accumulate), f32 elsewhere", "tf32-unfused": "tf32 convs (fp32 accumulate), f32 elsewhere",
-                      "fp32": "f32"}[args.precision],
+            "dtype": {"tf32x3": "tf32x3", "tf32": "tf32", "tf32-unfused": "tf32", "fp32": "f32"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": workload_name(args.generator, B), "precision": args.precision, "global_batch": B * world,
+            "config": {"workload": workload_name(args.generator, B), "precision": args.precision,
+                       "arithmetic": {"tf32x3": "encoder convs: tcgen05 TF32 products, 3-term error-compensated (fp32-equivalent), fp32 accumulate; FLAME / rasteriser f32",
+                                      "tf32": "encoder convs: tcgen05 TF32, fp32 accumulate; FLAME / rasteriser f32",
+                                      "tf32-unfused": "encoder convs: tcgen05 TF32, fp32 accumulate; FLAME / rasteriser f32",
+                                      "fp32": "f32 CUDA cores throughout"}[args.precision],
+                       "global_batch": B * world,
                        "faces_per_gpu_per_step": B, "image": "224x224 RGB fp32", "parallelism": "frame-shard dp%d" % world,
                        "l2_policy": "inputs rotate over a set of batches > 126 MB L2 (160 MB)",
                        "timing": "median of %d back-to-back windows of exactly %d steps (CUDA events, max over ranks per window)" % (head["windows"]["n"], K),
