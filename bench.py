@@ -343,6 +343,9 @@ def run_workload(cx, args, B, generator, slots, R, with_cpu):
         out["gather"] = {"backend": pipe._gather_backend,
                          "collective": "%s of %s per step, on a communication stream inside the timed region" % (how, "+".join(gather_keys)),
                          "recv_bytes_per_rank_per_step": gb, "recv_gbs_per_rank": gb / (out["ms_per_step"] * 1e-3) / 1e9}
+        p2p = getattr(pipe, "_p2p", None)
+        if pipe._gather_backend == "p2p" and isinstance(p2p, dict):
+            out["gather"]["form"] = "packed: one staging copy, one push per peer, lane released after the pack" if p2p.get("pack") else "direct: one push per (output, peer)"
         pipe.enable_gather(())
         ms3 = timed_windows(cx, dev_step, pipe.join, K, W, max(3, R // 2))
         ms4 = timed_windows(cx, host_step, pipe.join, K, W, max(3, R // 2))
